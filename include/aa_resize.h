@@ -1,0 +1,152 @@
+/*
+ * aa_resize.h -- C ABI of the B200-native anti-aliased separable resize (libaa_resize_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of vfdev-5/interpolate-antialiasing: everything
+ * below the pybind functions of step_two_dot_two/extension_interpolate.cpp.  Each entry point
+ * names the reference interface it replaces (file:line under /root/reference/step_two_dot_two/).
+ *
+ * Conventions
+ *   - plain C types only; no torch / C++ types cross this boundary;
+ *   - every function returns 0 (AA_OK) or a negative aa_status; aa_last_error() gives the
+ *     thread-local message; no C++ exception ever crosses the ABI;
+ *   - the caller owns every tensor buffer (torch allocates them); the library owns only the
+ *     per-device table cache, which is thread-safe;
+ *   - device entry points are asynchronous on the given stream and never synchronise, except on
+ *     a table-cache MISS (one tiny D2H of table metadata; call aa_warm_tables before CUDA-graph
+ *     capture);
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     AA_ERR_CUDA.
+ */
+#ifndef AA_RESIZE_H_
+#define AA_RESIZE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AA_RESIZE_ABI_VERSION 1
+
+typedef enum aa_status {
+  AA_OK = 0,
+  AA_ERR_INVALID = -1,     /* bad argument (shape, dtype, filter, null pointer)            */
+  AA_ERR_UNSUPPORTED = -2, /* valid but not implemented layout/dtype combination            */
+  AA_ERR_CUDA = -3,        /* CUDA runtime error (message has cudaGetErrorString)           */
+  AA_ERR_NOMEM = -4
+} aa_status;
+
+/* filter ids follow the reference's three helpers */
+typedef enum aa_filter {
+  AA_FILTER_BOX = 0,      /* nearest_forward ("it's not nearest but box") extension_interpolate.cpp:26-33,48;
+                             HelperInterpNearest aa_interpolation_impl.h:331-373 */
+  AA_FILTER_TRIANGLE = 1, /* linear_forward  extension_interpolate.cpp:7-14;  HelperInterpLinear :285-329 */
+  AA_FILTER_CUBIC = 2     /* cubic_forward   extension_interpolate.cpp:35-42; HelperInterpCubic  :375-425 */
+} aa_filter;
+
+typedef enum aa_dtype {
+  AA_U8 = 0,  /* input only: the uint8 -> float cast the reference's caller does (test.py:55,67) is fused */
+  AA_F32 = 1,
+  AA_F64 = 2
+} aa_dtype;
+
+/* execution-path selector for aa_resize_forward (flags argument) */
+#define AA_FLAG_AUTO 0u
+#define AA_FLAG_FORCE_GENERAL 1u /* gather-form tile kernel: H pass then V pass, no FMA contraction:
+                                    bit-identical to the reference for f32/f64                      */
+#define AA_FLAG_FORCE_STREAM 2u  /* streaming fused kernel (fails with AA_ERR_UNSUPPORTED if the
+                                    shape/layout is not eligible)                                   */
+#define AA_FLAG_STREAM_TMA 4u    /* streaming kernel: stage input rows with cp.async.bulk (TMA)     */
+#define AA_FLAG_STREAM_LDG 8u    /* streaming kernel: plain vectorised global loads                 */
+
+/* A 4-D tensor view [n, c, h, w] with ELEMENT strides, resident on CUDA device `device`.
+ * Supported layouts: channels_first (stride_w == 1) and channels_last (stride_c == 1,
+ * stride_w == c), both with dense rows; stride_n is free (batch slices are fine). */
+typedef struct aa_tensor_desc {
+  void* data;
+  int32_t dtype;  /* aa_dtype */
+  int32_t device; /* CUDA ordinal */
+  int64_t n, c, h, w;
+  int64_t stride_n, stride_c, stride_h, stride_w;
+} aa_tensor_desc;
+
+/* Per-axis tables in the reference's own representation (for bit-exactness checks). */
+typedef struct aa_tables_desc {
+  int64_t* xmin;     /* [out]       device, first input index of each output's window  (:254; the
+                                     reference stores xmin*stride_bytes :258, we store xmin)        */
+  int64_t* xsize;    /* [out]       device, window length                               (:255-257,:259) */
+  void* weights;     /* [out * K]   device, float (AA_F32) or double (AA_F64), normalised, zero padded
+                                     to K                                               (:262-278) */
+  int32_t interp_size; /* K, written by the call = (int)ceilf(support)*2+1              (:210) */
+} aa_tables_desc;
+
+/* ---- queries (host only, no device needed) ------------------------------------------------ */
+
+int aa_abi_version(void);
+const char* aa_last_error(void);
+
+/* K for one axis; replaces the `int& in_out_interp_size` result of
+ * HelperInterpBase::_compute_indices_weights_aa, aa_interpolation_impl.h:194-213.
+ * dtype selects the scalar_t the table arithmetic runs in (AA_U8 computes as AA_F32). */
+int aa_interp_size(int64_t in_size, int64_t out_size, int filter, int align_corners, int dtype,
+                   int32_t* interp_size_out);
+
+/* ---- tables -------------------------------------------------------------------------------- */
+
+/* Builds one axis' tables with the sm_100a table kernel and copies them, in the reference's
+ * representation, into caller-provided DEVICE buffers.  Replaces
+ * HelperInterp{Linear,Cubic,Nearest}::compute_indices_weights, aa_interpolation_impl.h:302-328,
+ * :337-363, :379-405 (+ :194-281).  Integer tables and weights are bit-exact. */
+int aa_build_tables(int64_t in_size, int64_t out_size, int filter, int align_corners, int dtype,
+                    int device, aa_tables_desc* dst, void* cuda_stream);
+
+/* Pre-populates the table cache for a forward and/or backward call (so that the real calls never
+ * synchronise, e.g. under CUDA-graph capture). */
+int aa_warm_tables(int64_t in_h, int64_t in_w, int64_t out_h, int64_t out_w, int filter,
+                   int align_corners, int dtype, int device, void* cuda_stream);
+
+/* Drops every cached table on every device (frees device memory). */
+int aa_clear_table_cache(void);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+
+/* out[n,c,oy,ox] = sum_y sum_x Wh[oy,y] * Ww[ox,x] * in[n,c,y,x]   (horizontal then vertical in the
+ * general path, as the reference; see DESIGN.md for the streaming path's order).
+ * Replaces ti_upsample_{bilinear,bicubic,nearest}2d_cpu, aa_interpolation_impl.h:731-807, i.e.
+ * the body of linear_forward / cubic_forward / nearest_forward, for already-allocated outputs.
+ * in->dtype: AA_U8 | AA_F32 | AA_F64; out->dtype: AA_F32 (for u8/f32 inputs) or AA_F64 (f64).
+ * n, c must match; in and out must be in the same memory format.  n == 0 is a no-op. */
+int aa_resize_forward(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter,
+                      int align_corners, uint32_t flags, void* cuda_stream);
+
+/* grad_in = Wh^T * grad_out * Ww : the true adjoint of aa_resize_forward, gather form, no atomics,
+ * no zero-fill pass.  Replaces ti_upsample_bilinear2d_backward_cpu,
+ * aa_interpolation_backward_impl.h:185-219 (linear_backward), whose body is the NON-antialiased
+ * adjoint; also provides the cubic/box backward the reference stubs out
+ * (test.py:111-116). */
+int aa_resize_backward(const aa_tensor_desc* grad_out, const aa_tensor_desc* grad_in, int filter,
+                       int align_corners, uint32_t flags, void* cuda_stream);
+
+/* The reference's exported linear_backward arithmetic (non-AA 2-tap bilinear adjoint,
+ * aa_interpolation_backward_impl.h:80-108), gather form.  Kept only so `linear_backward(...,
+ * antialias semantics of the reference)` can be reproduced bit-compatibly when asked. */
+int aa_resize_backward_nonaa_bilinear(const aa_tensor_desc* grad_out, const aa_tensor_desc* grad_in,
+                                      int align_corners, void* cuda_stream);
+
+/* ---- host-buffer convenience (what a non-torch host binds; used by bench.py's e2e) ---------- */
+
+/* Same as aa_resize_forward but `in`/`out` describe HOST buffers (device field = target CUDA
+ * ordinal).  The batch is cut into chunks that are copied H2D, resized and copied back D2H on
+ * rotating streams so copies overlap compute; returns after the last byte of `out` is written.
+ * Pinned host memory is recommended (pageable works, slower). */
+int aa_resize_forward_host(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter,
+                           int align_corners, uint32_t flags);
+
+/* Number of this library's kernel launches issued by the calling thread since the last reset
+ * (bench.py reports it as gpu_launches). */
+int64_t aa_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AA_RESIZE_H_ */

@@ -1,0 +1,75 @@
+"""interpolate_antialiasing_b200 -- B200-native (sm_100a) anti-aliased bilinear/bicubic resize.
+
+Drop-in for ONE hot path of vfdev-5/interpolate-antialiasing: the functions below have the names,
+positional signatures and semantics of the reference's pybind module
+(/root/reference/step_two_dot_two/extension_interpolate.cpp:46-51) and are backed by the torch C++
+extension in csrc/torch_binding.cpp, which calls the C ABI in include/aa_resize.h, which launches
+hand-written CUDA kernels.  There is no CPU path and no PyTorch fallback: importing works anywhere,
+calling needs the built extension and a CUDA device and fails loudly otherwise.
+
+    import interpolate_antialiasing_b200 as aa
+    y = aa.linear_forward(x_cuda, (oH, oW), False)
+    aa_interp = aa.load()          # the pybind module itself, e.g. to pass to the reference's test.py helpers
+"""
+import importlib.util
+import os
+
+from . import capi
+from ._build_ext import EXT, EXT_NAME, LIB
+
+__all__ = ["load", "linear_forward", "cubic_forward", "nearest_forward", "linear_backward", "cubic_backward",
+           "nearest_backward", "linear_backward_nonaa", "forward_with_flags", "AAResize", "aa_resize", "capi"]
+
+_ext = None
+
+
+def load():
+    """Returns the compiled pybind module (same exported names as the reference's `aa_interp`)."""
+    global _ext
+    if _ext is None:
+        if not os.path.exists(EXT) or not os.path.exists(LIB):
+            raise capi.AAError(
+                f"native extension not built ({EXT}); run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU or PyTorch fallback for this op.")
+        import torch  # noqa: F401
+        capi.lib()  # load libaa_resize_b200.so first (RTLD_GLOBAL) so the extension binds to it
+        spec = importlib.util.spec_from_file_location(EXT_NAME, EXT)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _ext = mod
+    return _ext
+
+
+def linear_forward(input, output_size, align_corners=False):
+    return load().linear_forward(input, list(output_size), align_corners)
+
+
+def cubic_forward(input, output_size, align_corners=False):
+    return load().cubic_forward(input, list(output_size), align_corners)
+
+
+def nearest_forward(input, output_size, align_corners=False):
+    return load().nearest_forward(input, list(output_size), align_corners)
+
+
+def linear_backward(grad_output, output_size, input_size, align_corners=False):
+    return load().linear_backward(grad_output, list(output_size), list(input_size), align_corners)
+
+
+def cubic_backward(grad_output, output_size, input_size, align_corners=False):
+    return load().cubic_backward(grad_output, list(output_size), list(input_size), align_corners)
+
+
+def nearest_backward(grad_output, output_size, input_size, align_corners=False):
+    return load().nearest_backward(grad_output, list(output_size), list(input_size), align_corners)
+
+
+def linear_backward_nonaa(grad_output, output_size, input_size, align_corners=False):
+    return load().linear_backward_nonaa(grad_output, list(output_size), list(input_size), align_corners)
+
+
+def forward_with_flags(input, output_size, align_corners, filter, flags):
+    return load().forward_with_flags(input, list(output_size), align_corners, capi.FILTERS.get(filter, filter), flags)
+
+
+from .functional import AAResize, aa_resize  # noqa: E402

@@ -1,0 +1,153 @@
+"""ctypes binding of the C ABI (include/aa_resize.h) -- the same calls a cgo/JNI/FFI host makes.
+
+The parity tests (`-m gpu`) go through this module so that they exercise the C-ABI entry points
+directly; torch is used only to allocate device memory and hand over raw pointers.
+There is no fallback: a missing library raises at import of the symbol table.
+"""
+import ctypes
+import os
+
+from ._build_ext import LIB
+
+BOX, TRIANGLE, CUBIC = 0, 1, 2
+U8, F32, F64 = 0, 1, 2
+FLAG_AUTO, FLAG_FORCE_GENERAL, FLAG_FORCE_STREAM, FLAG_STREAM_TMA, FLAG_STREAM_LDG = 0, 1, 2, 4, 8
+FILTERS = {"nearest": BOX, "box": BOX, "bilinear": TRIANGLE, "linear": TRIANGLE, "bicubic": CUBIC, "cubic": CUBIC}
+
+EXPORTS = [
+    "aa_abi_version", "aa_last_error", "aa_interp_size", "aa_build_tables", "aa_warm_tables",
+    "aa_clear_table_cache", "aa_resize_forward", "aa_resize_backward",
+    "aa_resize_backward_nonaa_bilinear", "aa_resize_forward_host", "aa_launch_count",
+]
+
+
+class TensorDesc(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("dtype", ctypes.c_int32), ("device", ctypes.c_int32),
+                ("n", ctypes.c_int64), ("c", ctypes.c_int64), ("h", ctypes.c_int64), ("w", ctypes.c_int64),
+                ("stride_n", ctypes.c_int64), ("stride_c", ctypes.c_int64), ("stride_h", ctypes.c_int64),
+                ("stride_w", ctypes.c_int64)]
+
+
+class TablesDesc(ctypes.Structure):
+    _fields_ = [("xmin", ctypes.c_void_p), ("xsize", ctypes.c_void_p), ("weights", ctypes.c_void_p),
+                ("interp_size", ctypes.c_int32)]
+
+
+class AAError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Loads libaa_resize_b200.so (RTLD_GLOBAL so the torch extension resolves against it)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            raise AAError(f"{LIB} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU or PyTorch fallback)")
+        L = ctypes.CDLL(LIB, mode=ctypes.RTLD_GLOBAL)
+        i32, i64, u32, vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p
+        P = ctypes.POINTER
+        L.aa_abi_version.restype = i32
+        L.aa_last_error.restype = ctypes.c_char_p
+        L.aa_interp_size.argtypes = [i64, i64, i32, i32, i32, P(i32)]
+        L.aa_build_tables.argtypes = [i64, i64, i32, i32, i32, i32, P(TablesDesc), vp]
+        L.aa_warm_tables.argtypes = [i64, i64, i64, i64, i32, i32, i32, i32, vp]
+        L.aa_resize_forward.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, u32, vp]
+        L.aa_resize_backward.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, u32, vp]
+        L.aa_resize_backward_nonaa_bilinear.argtypes = [P(TensorDesc), P(TensorDesc), i32, vp]
+        L.aa_resize_forward_host.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, u32]
+        L.aa_launch_count.argtypes = [i32]
+        L.aa_launch_count.restype = i64
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise AAError(f"aa_resize error {rc}: {lib().aa_last_error().decode()}")
+
+
+def _dtype_code(t):
+    import torch
+    return {torch.uint8: U8, torch.float32: F32, torch.float64: F64}[t.dtype]
+
+
+def desc(t, device=None):
+    """TensorDesc for a 4-D torch tensor (CUDA, or host when `device` is given)."""
+    assert t.dim() == 4
+    dev = t.device.index if t.is_cuda else device
+    return TensorDesc(t.data_ptr() if t.numel() else None, _dtype_code(t), dev, *t.shape, *t.stride())
+
+
+def _stream(t):
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _filter(f):
+    return FILTERS[f] if isinstance(f, str) else int(f)
+
+
+def interp_size(in_size, out_size, filter, align_corners=False, dtype=F32):
+    k = ctypes.c_int32(0)
+    check(lib().aa_interp_size(in_size, out_size, _filter(filter), int(align_corners), dtype, ctypes.byref(k)))
+    return k.value
+
+
+def build_tables(in_size, out_size, filter, align_corners=False, dtype=None, device=0):
+    """-> (xmin int64[out], xsize int64[out], weights [out, K]) as CUDA tensors, built by the table kernel."""
+    import torch
+    dtype = dtype or torch.float32
+    code = F64 if dtype == torch.float64 else F32
+    K = interp_size(in_size, out_size, filter, align_corners, code)
+    dev = torch.device("cuda", device)
+    xmin = torch.empty(out_size, dtype=torch.int64, device=dev)
+    xsize = torch.empty(out_size, dtype=torch.int64, device=dev)
+    w = torch.empty((out_size, K), dtype=dtype, device=dev)
+    td = TablesDesc(xmin.data_ptr(), xsize.data_ptr(), w.data_ptr(), 0)
+    with torch.cuda.device(dev):
+        check(lib().aa_build_tables(in_size, out_size, _filter(filter), int(align_corners), code, device,
+                                    ctypes.byref(td), _stream(xmin)))
+    assert td.interp_size == K
+    return xmin, xsize, w
+
+
+def resize_forward(x, output_size, filter, align_corners=False, flags=FLAG_AUTO, out=None):
+    """C-ABI forward on a CUDA tensor already contiguous in channels_first or channels_last."""
+    import torch
+    N, C, H, W = x.shape
+    oH, oW = int(output_size[0]), int(output_size[1])
+    if out is None:
+        cl = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+        out = torch.empty((N, C, oH, oW), dtype=torch.float64 if x.dtype == torch.float64 else torch.float32,
+                          device=x.device, memory_format=torch.channels_last if cl else torch.contiguous_format)
+    di, do = desc(x), desc(out)
+    check(lib().aa_resize_forward(ctypes.byref(di), ctypes.byref(do), _filter(filter), int(align_corners), flags, _stream(x)))
+    return out
+
+
+def resize_backward(grad_out, input_size, filter, align_corners=False, nonaa=False):
+    import torch
+    cl = grad_out.is_contiguous(memory_format=torch.channels_last) and not grad_out.is_contiguous()
+    gin = torch.empty(tuple(input_size), dtype=grad_out.dtype, device=grad_out.device,
+                      memory_format=torch.channels_last if cl else torch.contiguous_format)
+    dg, di = desc(grad_out), desc(gin)
+    if nonaa:
+        check(lib().aa_resize_backward_nonaa_bilinear(ctypes.byref(dg), ctypes.byref(di), int(align_corners), _stream(grad_out)))
+    else:
+        check(lib().aa_resize_backward(ctypes.byref(dg), ctypes.byref(di), _filter(filter), int(align_corners), 0, _stream(grad_out)))
+    return gin
+
+
+def resize_forward_host(x_host, out_host, filter, align_corners=False, flags=FLAG_AUTO, device=0):
+    """Host-buffer entry point (H2D, resize, D2H inside the call); tensors are CPU tensors, ideally pinned."""
+    di, do = desc(x_host, device), desc(out_host, device)
+    check(lib().aa_resize_forward_host(ctypes.byref(di), ctypes.byref(do), _filter(filter), int(align_corners), flags))
+    return out_host
+
+
+def launch_count(reset=False):
+    return lib().aa_launch_count(int(reset))

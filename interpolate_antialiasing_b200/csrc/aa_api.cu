@@ -1,0 +1,313 @@
+// aa_api.cu -- the C ABI (include/aa_resize.h): validation, table cache lookups, path selection.
+// No torch types, no exceptions across the boundary, no CPU fallback.
+#include <string.h>
+
+#include <mutex>
+
+#include "aa_common.cuh"
+
+namespace aa {
+
+static thread_local std::string g_err;
+static thread_local int64_t g_launches = 0;
+
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " (" + cudaGetErrorName(e) + ") at " + what;
+  return e == cudaErrorMemoryAllocation ? AA_ERR_NOMEM : AA_ERR_CUDA;
+}
+void count_launch(int n) { g_launches += n; }
+
+int classify_layout(const aa_tensor_desc& t, bool prefer_channels_last, Layout* L, bool* is_cl_out) {
+  // strides of size-1 dimensions carry no information
+  const bool cf = (t.w == 1 || t.stride_w == 1);
+  const bool cl = (t.c == 1 || t.stride_c == 1) && (t.w == 1 || t.stride_w == t.c);
+  bool use_cl;
+  if (cf && cl) use_cl = prefer_channels_last;
+  else if (cl) use_cl = true;
+  else if (cf) use_cl = false;
+  else return fail(AA_ERR_UNSUPPORTED, "tensor is neither channels_first (stride_w == 1) nor channels_last "
+                                       "(stride_c == 1, stride_w == c); make it contiguous in one of the two formats");
+  Layout r;
+  if (use_cl) {
+    r.planes = t.n; r.Cp = 1; r.Ci = (int)t.c; r.stride_n = t.stride_n; r.stride_p = 0;
+    r.stride_h = (t.h == 1) ? t.w * t.c : t.stride_h;
+    if (r.stride_h < t.w * t.c) return fail(AA_ERR_UNSUPPORTED, "channels_last rows overlap (stride_h < w*c)");
+  } else {
+    r.planes = t.n * t.c; r.Cp = (int)t.c; r.Ci = 1; r.stride_n = t.stride_n; r.stride_p = (t.c == 1) ? 0 : t.stride_c;
+    r.stride_h = (t.h == 1) ? t.w : t.stride_h;
+    if (r.stride_h < t.w) return fail(AA_ERR_UNSUPPORTED, "channels_first rows overlap (stride_h < w)");
+  }
+  *L = r;
+  if (is_cl_out) *is_cl_out = use_cl;
+  return AA_OK;
+}
+
+namespace {
+
+int check_desc(const aa_tensor_desc* t, const char* name) {
+  if (!t) return fail(AA_ERR_INVALID, std::string(name) + " is null");
+  if (t->n < 0 || t->c <= 0 || t->h <= 0 || t->w <= 0)
+    return fail(AA_ERR_INVALID, std::string("Non-empty 4D data tensor expected but got ") + name + " with sizes [" +
+                                    std::to_string(t->n) + ", " + std::to_string(t->c) + ", " + std::to_string(t->h) + ", " +
+                                    std::to_string(t->w) + "]");
+  if (t->n > 0 && !t->data) return fail(AA_ERR_INVALID, std::string(name) + ".data is null");
+  if (t->dtype != AA_U8 && t->dtype != AA_F32 && t->dtype != AA_F64) return fail(AA_ERR_INVALID, std::string(name) + ": bad dtype");
+  return AA_OK;
+}
+int check_filter(int filter) {
+  if (filter != AA_FILTER_BOX && filter != AA_FILTER_TRIANGLE && filter != AA_FILTER_CUBIC)
+    return fail(AA_ERR_INVALID, "filter must be 0 (box), 1 (triangle) or 2 (cubic)");
+  return AA_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    ok = err == cudaSuccess;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+BandedAxis fwd_axis(const AxisTables* t) { return BandedAxis{t->xmin, t->xsize, t->w, t->K, t->in, t->out}; }
+BandedAxis adj_axis(const AxisTables* t) { return BandedAxis{t->omin, t->osize, t->wT, t->KT, t->out, t->in}; }
+
+__global__ void widen_i32_i64(const int32_t* __restrict__ a, int64_t* __restrict__ b, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) b[i] = a[i];
+}
+
+int forward_impl(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align, uint32_t flags,
+                 cudaStream_t stream) {
+  int rc;
+  if ((rc = check_desc(in, "input")) != AA_OK) return rc;
+  if ((rc = check_desc(out, "output")) != AA_OK) return rc;
+  if ((rc = check_filter(filter)) != AA_OK) return rc;
+  if (in->n != out->n || in->c != out->c) return fail(AA_ERR_INVALID, "input and output must agree in n and c");
+  if (in->device != out->device) return fail(AA_ERR_INVALID, "input and output must live on the same device");
+  const int tdtype = in->dtype == AA_F64 ? AA_F64 : AA_F32;
+  if (out->dtype != tdtype) return fail(AA_ERR_INVALID, "output dtype must be f32 for u8/f32 inputs and f64 for f64 inputs");
+  if (in->n == 0) return AA_OK;  // empty batch is allowed (aa_interpolation_impl.h:747-750)
+  Layout lin, lout;
+  bool in_cl = false, out_cl = false;
+  if ((rc = classify_layout(*in, /*prefer_cl=*/false, &lin, &in_cl)) != AA_OK) return rc;
+  if ((rc = classify_layout(*out, in_cl, &lout, &out_cl)) != AA_OK) return rc;
+  if (in_cl != out_cl) {
+    // ambiguous input (e.g. c == 1): retry with the output's format
+    if ((rc = classify_layout(*in, out_cl, &lin, &in_cl)) != AA_OK) return rc;
+    if (in_cl != out_cl) return fail(AA_ERR_UNSUPPORTED, "input and output must use the same memory format");
+  }
+  DeviceGuard g(in->device);
+  if (!g.ok) return cuda_fail(g.err, "cudaSetDevice");
+  std::shared_ptr<AxisTables> th, tw;
+  if ((rc = get_axis_tables(in->device, in->h, out->h, filter, align, tdtype, stream, &th)) != AA_OK) return rc;
+  if ((rc = get_axis_tables(in->device, in->w, out->w, filter, align, tdtype, stream, &tw)) != AA_OK) return rc;
+  if (!(flags & AA_FLAG_FORCE_GENERAL) && tdtype == AA_F32) {
+    rc = launch_stream(in->data, in->dtype, lin, out->data, lout, th.get(), tw.get(), in->h, in->w, out->h, out->w,
+                       flags, stream);
+    if (rc == AA_OK) return rc;
+    if (rc != AA_ERR_UNSUPPORTED || (flags & AA_FLAG_FORCE_STREAM)) return rc;
+  } else if (flags & AA_FLAG_FORCE_STREAM) {
+    return fail(AA_ERR_UNSUPPORTED, "stream path: f32/u8 only");
+  }
+  return launch_general(in->data, in->dtype, lin, out->data, out->dtype, lout, fwd_axis(th.get()), fwd_axis(tw.get()),
+                        /*exact=*/true, stream);
+}
+
+int backward_check(const aa_tensor_desc* gout, const aa_tensor_desc* gin, Layout* lo, Layout* li) {
+  int rc;
+  if ((rc = check_desc(gout, "grad_output")) != AA_OK) return rc;
+  if ((rc = check_desc(gin, "grad_input")) != AA_OK) return rc;
+  if (gout->n != gin->n || gout->c != gin->c) return fail(AA_ERR_INVALID, "grad_output and grad_input must agree in n and c");
+  if (gout->device != gin->device) return fail(AA_ERR_INVALID, "grad tensors must live on the same device");
+  if (gout->dtype == AA_U8 || gout->dtype != gin->dtype) return fail(AA_ERR_INVALID, "backward: f32 or f64, same dtype on both sides");
+  bool o_cl = false, i_cl = false;
+  if ((rc = classify_layout(*gout, false, lo, &o_cl)) != AA_OK) return rc;
+  if ((rc = classify_layout(*gin, o_cl, li, &i_cl)) != AA_OK) return rc;
+  if (o_cl != i_cl) {
+    if ((rc = classify_layout(*gout, i_cl, lo, &o_cl)) != AA_OK) return rc;
+    if (o_cl != i_cl) return fail(AA_ERR_UNSUPPORTED, "grad_output and grad_input must use the same memory format");
+  }
+  return AA_OK;
+}
+
+}  // namespace
+}  // namespace aa
+
+using namespace aa;
+
+extern "C" {
+
+int aa_abi_version(void) { return AA_RESIZE_ABI_VERSION; }
+const char* aa_last_error(void) { return g_err.c_str(); }
+
+int64_t aa_launch_count(int reset) {
+  int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+int aa_interp_size(int64_t in_size, int64_t out_size, int filter, int align_corners, int dtype, int32_t* k) {
+  int rc;
+  if ((rc = check_filter(filter)) != AA_OK) return rc;
+  if (!k || in_size <= 0 || out_size <= 0) return fail(AA_ERR_INVALID, "aa_interp_size: bad arguments");
+  *k = host_interp_size(in_size, out_size, filter, align_corners, dtype == AA_F64 ? AA_F64 : AA_F32);
+  return AA_OK;
+}
+
+int aa_build_tables(int64_t in_size, int64_t out_size, int filter, int align_corners, int dtype, int device,
+                    aa_tables_desc* dst, void* cuda_stream) {
+  int rc;
+  if ((rc = check_filter(filter)) != AA_OK) return rc;
+  if (!dst || !dst->xmin || !dst->xsize || !dst->weights) return fail(AA_ERR_INVALID, "aa_build_tables: null destination");
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  DeviceGuard g(device);
+  if (!g.ok) return cuda_fail(g.err, "cudaSetDevice");
+  std::shared_ptr<AxisTables> t;
+  const int td = dtype == AA_F64 ? AA_F64 : AA_F32;
+  if ((rc = get_axis_tables(device, in_size, out_size, filter, align_corners, td, stream, &t)) != AA_OK) return rc;
+  const int NT = 256;
+  widen_i32_i64<<<(unsigned)((out_size + NT - 1) / NT), NT, 0, stream>>>(t->xmin, dst->xmin, out_size);
+  AA_LAUNCH_CHECK("widen xmin");
+  widen_i32_i64<<<(unsigned)((out_size + NT - 1) / NT), NT, 0, stream>>>(t->xsize, dst->xsize, out_size);
+  AA_LAUNCH_CHECK("widen xsize");
+  AA_CUDA_TRY(cudaMemcpyAsync(dst->weights, t->w, (size_t)(td == AA_F64 ? 8 : 4) * out_size * t->K,
+                              cudaMemcpyDeviceToDevice, stream));
+  dst->interp_size = t->K;
+  return AA_OK;
+}
+
+int aa_warm_tables(int64_t in_h, int64_t in_w, int64_t out_h, int64_t out_w, int filter, int align_corners, int dtype,
+                   int device, void* cuda_stream) {
+  int rc;
+  if ((rc = check_filter(filter)) != AA_OK) return rc;
+  DeviceGuard g(device);
+  if (!g.ok) return cuda_fail(g.err, "cudaSetDevice");
+  std::shared_ptr<AxisTables> t;
+  const int td = dtype == AA_F64 ? AA_F64 : AA_F32;
+  if ((rc = get_axis_tables(device, in_h, out_h, filter, align_corners, td, (cudaStream_t)cuda_stream, &t)) != AA_OK) return rc;
+  if (td == AA_F32 && t->kt_max <= 6) {
+    rc = ensure_slot_tables(t.get(), t->kt_max <= 3 ? 3 : t->kt_max, (cudaStream_t)cuda_stream);
+    if (rc != AA_OK && rc != AA_ERR_UNSUPPORTED) return rc;
+  }
+  return get_axis_tables(device, in_w, out_w, filter, align_corners, td, (cudaStream_t)cuda_stream, &t);
+}
+
+int aa_clear_table_cache(void) { return clear_table_cache(); }
+
+int aa_resize_forward(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align_corners, uint32_t flags,
+                      void* cuda_stream) {
+  return forward_impl(in, out, filter, align_corners, flags, (cudaStream_t)cuda_stream);
+}
+
+int aa_resize_backward(const aa_tensor_desc* gout, const aa_tensor_desc* gin, int filter, int align_corners, uint32_t flags,
+                       void* cuda_stream) {
+  (void)flags;
+  int rc;
+  Layout lo, li;
+  if ((rc = check_filter(filter)) != AA_OK) return rc;
+  if ((rc = backward_check(gout, gin, &lo, &li)) != AA_OK) return rc;
+  if (gout->n == 0) return AA_OK;
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  DeviceGuard g(gout->device);
+  if (!g.ok) return cuda_fail(g.err, "cudaSetDevice");
+  std::shared_ptr<AxisTables> th, tw;
+  if ((rc = get_axis_tables(gout->device, gin->h, gout->h, filter, align_corners, gout->dtype, stream, &th)) != AA_OK) return rc;
+  if ((rc = get_axis_tables(gout->device, gin->w, gout->w, filter, align_corners, gout->dtype, stream, &tw)) != AA_OK) return rc;
+  return launch_general(gout->data, gout->dtype, lo, gin->data, gin->dtype, li, adj_axis(th.get()), adj_axis(tw.get()),
+                        /*exact=*/false, stream);
+}
+
+int aa_resize_backward_nonaa_bilinear(const aa_tensor_desc* gout, const aa_tensor_desc* gin, int align_corners,
+                                      void* cuda_stream) {
+  int rc;
+  Layout lo, li;
+  if ((rc = backward_check(gout, gin, &lo, &li)) != AA_OK) return rc;
+  if (gout->n == 0) return AA_OK;
+  DeviceGuard g(gout->device);
+  if (!g.ok) return cuda_fail(g.err, "cudaSetDevice");
+  return launch_backward_nonaa(gout->data, gin->data, gout->dtype, lo, li, gout->h, gout->w, gin->h, gin->w, align_corners,
+                               (cudaStream_t)cuda_stream);
+}
+
+// ---- host-buffer entry: chunked H2D -> resize -> D2H on rotating streams --------------------------
+namespace {
+struct HostCtx {
+  static constexpr int NS = 3;
+  cudaStream_t streams[NS] = {};
+  void* din[NS] = {};
+  void* dout[NS] = {};
+  size_t cap_in = 0, cap_out = 0;
+  bool init = false;
+};
+std::mutex g_host_mu;
+HostCtx g_host_ctx[64];
+}  // namespace
+
+int aa_resize_forward_host(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align_corners,
+                           uint32_t flags) {
+  int rc;
+  if ((rc = check_desc(in, "input")) != AA_OK) return rc;
+  if ((rc = check_desc(out, "output")) != AA_OK) return rc;
+  if (in->n != out->n || in->c != out->c) return fail(AA_ERR_INVALID, "input and output must agree in n and c");
+  if (in->n == 0) return AA_OK;
+  const int dev = in->device;
+  if (dev < 0 || dev >= 64) return fail(AA_ERR_INVALID, "bad device ordinal");
+  const size_t ies = in->dtype == AA_U8 ? 1 : (in->dtype == AA_F32 ? 4 : 8);
+  const size_t oes = out->dtype == AA_F32 ? 4 : 8;
+  const size_t img_in = (size_t)in->c * in->h * in->w, img_out = (size_t)out->c * out->h * out->w;
+  if ((in->n > 1 && (size_t)in->stride_n != img_in) || (out->n > 1 && (size_t)out->stride_n != img_out))
+    return fail(AA_ERR_UNSUPPORTED, "host path needs densely packed images (stride_n == c*h*w)");
+  DeviceGuard g(dev);
+  if (!g.ok) return cuda_fail(g.err, "cudaSetDevice");
+  std::lock_guard<std::mutex> lock(g_host_mu);
+  HostCtx& C = g_host_ctx[dev];
+  if (!C.init) {
+    for (int i = 0; i < HostCtx::NS; i++) AA_CUDA_TRY(cudaStreamCreateWithFlags(&C.streams[i], cudaStreamNonBlocking));
+    C.init = true;
+  }
+  // chunk = as many images as fit ~96 MiB of input, at least 1, at most n/NS rounded up
+  int64_t per = (int64_t)((96ull << 20) / (img_in * ies));
+  if (per < 1) per = 1;
+  const int64_t even = (in->n + HostCtx::NS - 1) / HostCtx::NS;
+  if (per > even) per = even;
+  const size_t need_in = (size_t)per * img_in * ies, need_out = (size_t)per * img_out * oes;
+  if (need_in > C.cap_in || need_out > C.cap_out) {
+    for (int i = 0; i < HostCtx::NS; i++) {
+      AA_CUDA_TRY(cudaStreamSynchronize(C.streams[i]));
+      if (C.din[i]) cudaFree(C.din[i]);
+      if (C.dout[i]) cudaFree(C.dout[i]);
+      C.din[i] = C.dout[i] = nullptr;
+    }
+    C.cap_in = C.cap_out = 0;
+    for (int i = 0; i < HostCtx::NS; i++) {
+      AA_CUDA_TRY(cudaMalloc(&C.din[i], need_in));
+      AA_CUDA_TRY(cudaMalloc(&C.dout[i], need_out));
+    }
+    C.cap_in = need_in;
+    C.cap_out = need_out;
+  }
+  int64_t done = 0;
+  for (int i = 0; done < in->n; i++) {
+    const int s = i % HostCtx::NS;
+    const int64_t nb = std::min<int64_t>(per, in->n - done);
+    aa_tensor_desc di = *in, dd_out = *out;
+    di.data = C.din[s]; di.n = nb;
+    dd_out.data = C.dout[s]; dd_out.n = nb;
+    AA_CUDA_TRY(cudaMemcpyAsync(C.din[s], (const char*)in->data + (size_t)done * img_in * ies, (size_t)nb * img_in * ies,
+                                cudaMemcpyHostToDevice, C.streams[s]));
+    if ((rc = forward_impl(&di, &dd_out, filter, align_corners, flags, C.streams[s])) != AA_OK) return rc;
+    AA_CUDA_TRY(cudaMemcpyAsync((char*)out->data + (size_t)done * img_out * oes, C.dout[s], (size_t)nb * img_out * oes,
+                                cudaMemcpyDeviceToHost, C.streams[s]));
+    done += nb;
+  }
+  for (int i = 0; i < HostCtx::NS; i++) AA_CUDA_TRY(cudaStreamSynchronize(C.streams[i]));
+  return AA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,121 @@
+// aa_common.cuh -- shared declarations of the sm_100a anti-aliased resize library.
+// Internal header: nothing here crosses the C ABI (include/aa_resize.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/aa_resize.h"
+
+namespace aa {
+
+// ---- error plumbing (thread-local message, negative status codes) --------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+void count_launch(int n = 1);
+
+#define AA_CUDA_TRY(expr)                                        \
+  do {                                                           \
+    cudaError_t _e = (expr);                                     \
+    if (_e != cudaSuccess) return ::aa::cuda_fail(_e, #expr);    \
+  } while (0)
+
+#define AA_LAUNCH_CHECK(what)                                    \
+  do {                                                           \
+    ::aa::count_launch();                                        \
+    cudaError_t _e = cudaGetLastError();                         \
+    if (_e != cudaSuccess) return ::aa::cuda_fail(_e, what);     \
+  } while (0)
+
+// ---- per-axis tables -------------------------------------------------------------------------
+// Forward tables follow HelperInterpBase::_compute_indices_weights_aa
+// (/root/reference/step_two_dot_two/aa_interpolation_impl.h:194-281): for output index o the window
+// is input [xmin[o], xmin[o]+xsize[o]) with weights w[o*K + j].
+// Adjoint tables are the transpose: for input index x the outputs whose window covers x are the
+// contiguous range [omin[x], omin[x]+osize[x]) (xmin and xmin+xsize are non-decreasing in o) and
+// wT[x*KT + k] = w[(omin[x]+k)*K + (x - xmin[omin[x]+k])].
+struct AxisTables {
+  // key
+  int device = 0;
+  int64_t in = 0, out = 0;
+  int filter = 0, align = 0;
+  int dtype = AA_F32;  // AA_F32 or AA_F64: scalar_t of the table arithmetic
+  // host-side scalars (computed with the same IEEE operations as the device kernel)
+  float scale_f = 0.f, support_f = 0.f;
+  double scale_d = 0.0, support_d = 0.0;
+  int K = 0;         // padded taps per output (:210)
+  int KT = 0;        // adjoint row pitch (>= kt_max)
+  int kt_max = 0;    // max number of outputs covering one input index (measured on device)
+  int xsize_max = 0; // max window length (measured on device)
+  int monotone = 1;  // device-verified: xmin and xmin+xsize non-decreasing
+  // device buffers (one allocation, `block`)
+  void* block = nullptr;
+  int32_t* xmin = nullptr;   // [out]
+  int32_t* xsize = nullptr;  // [out]
+  void* w = nullptr;         // [out*K]  float | double
+  int32_t* omin = nullptr;   // [in]
+  int32_t* osize = nullptr;  // [in]
+  void* wT = nullptr;        // [in*KT]  float | double
+  // streaming slot tables (float only; built lazily for a given A)
+  int slot_A = 0;            // number of rotating accumulator slots
+  int slot_RS = 0;           // record stride in 32-bit words = roundup4(A+1)
+  float* slot = nullptr;     // [in][RS]: A weights by slot (o % A), then (first_flush_o | nflush<<24)
+  // host mirrors of the integer tables (for launch planning)
+  std::vector<int32_t> h_xmin, h_xsize;
+  cudaEvent_t ready = nullptr;  // recorded on the building stream
+  ~AxisTables();
+};
+
+// Returns the cached tables, building them on `stream` on a miss (one sync on a miss only).
+int get_axis_tables(int device, int64_t in, int64_t out, int filter, int align, int dtype,
+                    cudaStream_t stream, std::shared_ptr<AxisTables>* result);
+// Makes sure t->slot exists for at least `A` slots (A in {3,4,5,6,8}); may launch one tiny kernel.
+int ensure_slot_tables(AxisTables* t, int A, cudaStream_t stream);
+int clear_table_cache();
+// Host-only K computation (no device), same arithmetic as the table kernel.
+int host_interp_size(int64_t in, int64_t out, int filter, int align, int dtype);
+
+// ---- layout --------------------------------------------------------------------------------
+// Both supported memory formats are expressed as `planes` independent 2-D images whose rows are
+// flat arrays of W*Ci elements with the channel interleaved at stride 1:
+//   channels_first: planes = N*C, Ci = 1;   channels_last: planes = N, Ci = C.
+struct Layout {
+  int64_t planes = 0;  // number of independent 2-D planes
+  int Cp = 1;          // planes per batch element (C for channels_first, 1 for channels_last)
+  int Ci = 1;          // interleave factor along the flat row
+  int64_t stride_n = 0, stride_p = 0;  // element strides: plane p -> (p / Cp)*stride_n + (p % Cp)*stride_p
+  int64_t stride_h = 0;                // element stride between rows
+};
+// Classifies a tensor desc; returns AA_ERR_UNSUPPORTED for anything but dense-row NCHW/NHWC.
+int classify_layout(const aa_tensor_desc& t, bool prefer_channels_last, Layout* out, bool* is_channels_last);
+
+// ---- kernels' host launchers ---------------------------------------------------------------
+struct BandedAxis {  // one axis of a banded separable apply: out index i reads in [start[i], start[i]+size[i])
+  const int32_t* start;
+  const int32_t* size;
+  const void* w;  // [n_out * pitch]
+  int pitch;
+  int64_t n_in, n_out;
+};
+
+// General gather-form tile kernel: out = Ah * in * Aw^T per plane, horizontal pass first.
+// exact=true: separate multiply and add (bit-identical to the reference's C++), else FMA.
+int launch_general(const void* in, int in_dtype, const Layout& lin, void* out, int out_dtype,
+                   const Layout& lout, const BandedAxis& ah, const BandedAxis& aw, bool exact,
+                   cudaStream_t stream);
+
+// Streaming fused kernel (downsampling in both axes, f32/u8 in, f32 out).  Returns
+// AA_ERR_UNSUPPORTED when not eligible so the caller can fall back to launch_general.
+int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout,
+                  AxisTables* th, AxisTables* tw, int64_t H, int64_t W, int64_t oH, int64_t oW,
+                  uint32_t flags, cudaStream_t stream);
+
+int launch_backward_nonaa(const void* gout, void* gin, int dtype, const Layout& lout, const Layout& lin,
+                          int64_t oH, int64_t oW, int64_t H, int64_t W, int align, cudaStream_t stream);
+
+}  // namespace aa

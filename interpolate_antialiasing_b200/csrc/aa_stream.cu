@@ -1,0 +1,391 @@
+// aa_stream.cu -- K2: the fused streaming forward kernel (sm_100a), the bandwidth-bound hot path.
+//
+// Replaces the two TensorIterator passes + temp tensor of
+// ti_separable_upsample_generic_Nd_kernel_impl
+// (/root/reference/step_two_dot_two/aa_interpolation_impl.h:628-683) with ONE kernel that reads
+// every input element from HBM once and writes every output element once.
+//
+// Shape of the computation (see DESIGN.md section 4 for the why):
+//   * A plane row is a flat array of W*Ci elements (Ci = C for channels_last, 1 for channels_first),
+//     so the VERTICAL filter is layout-agnostic: thread t owns VEC consecutive flat elements and
+//     streams down the rows with 128-bit coalesced loads.  Each input row contributes to at most A
+//     output rows (A = 3 bilinear, 5 bicubic when downsampling), so the thread keeps A rotating
+//     accumulators per element: slot (oy % A) collects output row oy.  The per-row record
+//     {w[slot 0..A), first_flush_oy | nflush<<24} is warp-uniform (one 16/32-byte broadcast load).
+//   * When an output row's window ends, its accumulator (one vertically-filtered row, still at full
+//     input width) is flushed to shared memory.  Every G flushed rows the CTA runs the HORIZONTAL
+//     filter as a gather over the shared-memory rows (weights staged in shared memory, each weight
+//     reused for RPT rows) and writes G output rows with coalesced stores.
+//   * Work is split stream-K style: the (plane, column strip, output row) space is cut into
+//     gridDim.x equal contiguous ranges, one per persistent CTA; a CTA that starts mid-plane re-reads
+//     only the <= 2*support_h halo rows of its first window.
+//
+// Order of the passes is V then H (the reference is H then V).  Both orders evaluate the same
+// separable sum with fp32 rounding of the intermediate; the difference is pure rounding
+// (measured <= 1.3e-4 abs / 2.3e-6 rel on a 0..255 scale against the reference, tolerance
+// 1e-3 abs / 1e-5 rel -- tests/test_forward_gpu.py).  The bit-exact order lives in aa_general.cu.
+#include <algorithm>
+
+#include "aa_common.cuh"
+
+namespace aa {
+namespace {
+
+constexpr int kMaxA = 6;
+
+struct SParams {
+  const void* in;
+  float* out;
+  Layout lin, lout;
+  int Ci;
+  int64_t H, oH, oW;
+  const float* slot_h;  // [H][RS]
+  int RS;
+  const int32_t *xmin_h, *xsize_h;
+  const int32_t *xmin_w, *xsize_w;
+  const float* w_w;  // [oW][Kw]
+  int Kw;
+  int n_strips, strip_ox;
+  int64_t total_units;  // planes * n_strips * oH
+  int vw;               // shared-memory row pitch of Vs in floats
+  int vr;               // rows of Vs
+  int tg;               // buffered rows that trigger a horizontal phase
+};
+
+// ---- vector loads (read-once data: bypass L1 allocation) -------------------------------------
+template <typename in_t, int VEC> struct VLoad;
+template <> struct VLoad<float, 4> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+  }
+};
+template <> struct VLoad<float, 2> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[2]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "l"(p));
+  }
+};
+template <> struct VLoad<float, 1> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[1]) {
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v[0]) : "l"(p));
+  }
+};
+__device__ __forceinline__ void unpack4(uint32_t w, float* v) {
+  v[0] = (float)(w & 0xffu);
+  v[1] = (float)((w >> 8) & 0xffu);
+  v[2] = (float)((w >> 16) & 0xffu);
+  v[3] = (float)(w >> 24);
+}
+template <> struct VLoad<uint8_t, 16> {
+  static __device__ __forceinline__ void ld(const uint8_t* p, float (&v)[16]) {
+    uint32_t a, b, c, d;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
+    unpack4(a, v); unpack4(b, v + 4); unpack4(c, v + 8); unpack4(d, v + 12);
+  }
+};
+template <> struct VLoad<uint8_t, 8> {
+  static __device__ __forceinline__ void ld(const uint8_t* p, float (&v)[8]) {
+    uint32_t a, b;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
+    unpack4(a, v); unpack4(b, v + 4);
+  }
+};
+template <> struct VLoad<uint8_t, 4> {
+  static __device__ __forceinline__ void ld(const uint8_t* p, float (&v)[4]) {
+    uint32_t a;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(a) : "l"(p));
+    unpack4(a, v);
+  }
+};
+
+template <int A> struct Rec { float w[A]; int packed; };
+
+template <int A>
+__device__ __forceinline__ Rec<A> load_rec(const float* __restrict__ slot, int RS, int64_t y) {
+  Rec<A> r;
+  const float4* p = reinterpret_cast<const float4*>(slot + y * RS);
+  constexpr int NW = (A + 1 + 3) / 4;
+  float tmp[NW * 4];
+#pragma unroll
+  for (int i = 0; i < NW; i++) {
+    const float4 q = __ldg(p + i);
+    tmp[4 * i] = q.x; tmp[4 * i + 1] = q.y; tmp[4 * i + 2] = q.z; tmp[4 * i + 3] = q.w;
+  }
+#pragma unroll
+  for (int a = 0; a < A; a++) r.w[a] = tmp[a];
+  r.packed = __float_as_int(tmp[A]);
+  return r;
+}
+
+template <int VEC> __device__ __forceinline__ void store_vec(float* dst, const float* a) {
+  if constexpr (VEC % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < VEC / 4; i++)
+      reinterpret_cast<float4*>(dst)[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<float2*>(dst) = make_float2(a[0], a[1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; i++) dst[i] = a[i];
+  }
+}
+
+// A     rotating accumulator slots (>= max outputs covering one input row)
+// VEC   flat elements per thread per row
+// NT    threads per CTA
+// U     input rows in flight per thread
+// Shared memory holds up to P.vr vertically-filtered rows; the horizontal phase runs at the end of a
+// U-row batch once at least P.tg rows are buffered (host guarantees tg - 1 + max flushes per batch <= vr).
+template <int A, int VEC, typename in_t, int NT, int U>
+__global__ void __launch_bounds__(NT) aa_stream_kernel(const SParams P) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int RPT = 4;  // rows per thread in the horizontal phase
+  float* Vs = smem;                                  // [vr][vw]
+  float* Ws = Vs + (size_t)P.vr * P.vw;              // [strip_ox][Kw]
+  int* sxmin = reinterpret_cast<int*>(Ws + (size_t)P.strip_ox * P.Kw);  // [strip_ox]
+  int* sxsize = sxmin + P.strip_ox;                                      // [strip_ox]
+
+  const int t = threadIdx.x;
+  const int Ci = P.Ci;
+  const int64_t oH = P.oH;
+  const int64_t u_begin = P.total_units * (int64_t)blockIdx.x / gridDim.x;
+  const int64_t u_end = P.total_units * (int64_t)(blockIdx.x + 1) / gridDim.x;
+  int cur_strip = -1;
+
+  for (int64_t u = u_begin; u < u_end;) {
+    // ---- segment = run of output rows [oyA, oyB) inside one (plane, strip) column
+    const int64_t col = u / oH;
+    const int oyA = (int)(u - col * oH);
+    const int64_t seg_end = min(u_end, (col + 1) * oH);
+    const int oyB = oyA + (int)(seg_end - u);
+    const int64_t plane = col / P.n_strips;
+    const int s = (int)(col - plane * P.n_strips);
+    const int ox0 = s * P.strip_ox;
+    const int ox1 = min((int)P.oW, ox0 + P.strip_ox);
+    if (s != cur_strip) {
+      __syncthreads();
+      const int nox = ox1 - ox0;
+      for (int i = t; i < nox * P.Kw; i += NT) Ws[i] = __ldg(P.w_w + (int64_t)ox0 * P.Kw + i);
+      for (int i = t; i < nox; i += NT) { sxmin[i] = __ldg(P.xmin_w + ox0 + i); sxsize[i] = __ldg(P.xsize_w + ox0 + i); }
+      cur_strip = s;
+      __syncthreads();
+    }
+    const int fl0 = (sxmin[0] * Ci) & ~(VEC - 1);                            // first flat element of the strip
+    const int fl_end = (sxmin[ox1 - ox0 - 1] + sxsize[ox1 - ox0 - 1]) * Ci;  // one past the last
+    const int fmy = fl0 + VEC * t;
+    const bool valid = fmy < fl_end;
+    const in_t* ip = (const in_t*)P.in + (plane / P.lin.Cp) * P.lin.stride_n + (plane % P.lin.Cp) * P.lin.stride_p + fmy;
+    float* op = P.out + (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p + (int64_t)ox0 * Ci;
+    const int64_t yA = __ldg(P.xmin_h + oyA);
+    const int64_t yB = (int64_t)__ldg(P.xmin_h + oyB - 1) + __ldg(P.xsize_h + oyB - 1);
+    const int nof = (ox1 - ox0) * Ci;
+
+    float acc[A][VEC];
+#pragma unroll
+    for (int a = 0; a < A; a++)
+#pragma unroll
+      for (int i = 0; i < VEC; i++) acc[a][i] = 0.f;
+    int gbase = oyA;  // output row held in Vs[0]
+    int cnt = 0;      // rows buffered in Vs
+
+    for (int64_t y = yA; y < yB; y += U) {
+      float v[U][VEC];
+      Rec<A> rec[U];
+#pragma unroll
+      for (int i = 0; i < U; i++) {
+        if (y + i < yB) {
+          if (valid) VLoad<in_t, VEC>::ld(ip + (y + i) * P.lin.stride_h, v[i]);
+          else {
+#pragma unroll
+            for (int e = 0; e < VEC; e++) v[i][e] = 0.f;
+          }
+          rec[i] = load_rec<A>(P.slot_h, P.RS, y + i);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < U; i++) {
+        if (y + i < yB) {
+          // ---- vertical filter: A FMAs per element, weights warp-uniform
+#pragma unroll
+          for (int a = 0; a < A; a++)
+#pragma unroll
+            for (int e = 0; e < VEC; e++) acc[a][e] = fmaf(rec[i].w[a], v[i][e], acc[a][e]);
+          const int nfl = rec[i].packed >> 24;
+          if (nfl) {
+            const int fo = rec[i].packed & 0xffffff;
+#pragma unroll
+            for (int k = 0; k < A; k++) {
+              if (k < nfl) {
+                const int o = fo + k;
+                const int slot = o % A;
+                const bool inr = (o >= oyA) && (o < oyB);
+                float* dst = Vs + (size_t)cnt * P.vw + VEC * t;
+#pragma unroll
+                for (int a = 0; a < A; a++) {
+                  if (a == slot) {
+                    if (inr && valid) store_vec<VEC>(dst, acc[a]);
+#pragma unroll
+                    for (int e = 0; e < VEC; e++) acc[a][e] = 0.f;
+                  }
+                }
+                if (inr) cnt++;
+              }
+            }
+          }
+        }
+      }
+      if (cnt >= P.tg || (y + U >= yB && cnt > 0)) {
+        // ---- horizontal filter over the buffered rows [gbase, gbase+cnt)
+        __syncthreads();
+        const int nrg = (cnt + RPT - 1) / RPT;
+        for (int item = t; item < nof * nrg; item += NT) {
+          const int rg = item / nof;
+          const int cf = item - rg * nof;  // flat output column inside the strip
+          const int oxl = cf / Ci;
+          const int c = cf - oxl * Ci;
+          const int xs = sxsize[oxl];
+          const float* wr = Ws + oxl * P.Kw;
+          const float* vs = Vs + (size_t)(rg * RPT) * P.vw + (sxmin[oxl] * Ci + c - fl0);
+          float h[RPT];
+#pragma unroll
+          for (int r = 0; r < RPT; r++) h[r] = 0.f;
+          for (int j = 0; j < xs; j++) {
+            const float wj = wr[j];
+#pragma unroll
+            for (int r = 0; r < RPT; r++) h[r] = fmaf(wj, vs[(size_t)r * P.vw + j * Ci], h[r]);
+          }
+#pragma unroll
+          for (int r = 0; r < RPT; r++) {
+            const int row = rg * RPT + r;
+            if (row < cnt) op[(int64_t)(gbase + row) * P.lout.stride_h + cf] = h[r];
+          }
+        }
+        __syncthreads();
+        gbase += cnt;
+        cnt = 0;
+      }
+    }
+    u = seg_end;
+  }
+}
+
+template <int A, int VEC, typename in_t>
+struct Cfg {
+  static constexpr int NT = 256;
+  static constexpr int U = 4;
+  static constexpr int TG = 8;  // buffered rows that trigger a horizontal phase
+};
+
+template <int A, int VEC, typename in_t>
+int launch_cfg(SParams& P, const AxisTables* th, const AxisTables* tw, int device, cudaStream_t stream) {
+  using C = Cfg<A, VEC, in_t>;
+  auto kern = aa_stream_kernel<A, VEC, in_t, C::NT, C::U>;
+  const int cap = C::NT * VEC;  // flat elements one strip may span
+  // ---- strip plan: as few, equal strips as fit `cap` flat elements (exact, from host tables)
+  const int64_t oW = P.oW;
+  const int Ci = P.Ci;
+  int n_strips = 1, strip_ox = (int)oW;
+  int64_t max_extent = 0;
+  for (;; n_strips++) {
+    if (n_strips > oW) return fail(AA_ERR_UNSUPPORTED, "stream: a single output column spans more than one strip");
+    strip_ox = (int)((oW + n_strips - 1) / n_strips);
+    bool ok = strip_ox <= 512;
+    max_extent = 0;
+    for (int64_t a = 0; ok && a < oW; a += strip_ox) {
+      const int64_t b = std::min<int64_t>(oW, a + strip_ox) - 1;
+      const int64_t f0 = ((int64_t)tw->h_xmin[a] * Ci) & ~(int64_t)(VEC - 1);
+      const int64_t f1 = ((int64_t)tw->h_xmin[b] + tw->h_xsize[b]) * Ci;
+      if (f1 - f0 > cap) ok = false;
+      max_extent = std::max(max_extent, f1 - f0);
+    }
+    if (ok) break;
+  }
+  n_strips = (int)((oW + strip_ox - 1) / strip_ox);
+  P.n_strips = n_strips;
+  P.strip_ox = strip_ox;
+  constexpr int VA = VEC > 4 ? VEC : 4;
+  P.vw = (int)((max_extent + VA - 1) / VA * VA);
+  // ---- row buffer plan: most rows that can finish inside one U-row batch (exact, from host tables)
+  int fmax = 1;
+  {
+    const int64_t oH = P.oH;
+    int64_t lo = 0;
+    for (int64_t o = 0; o < oH; o++) {  // ends are non-decreasing
+      const int64_t e = (int64_t)th->h_xmin[o] + th->h_xsize[o];
+      while ((int64_t)th->h_xmin[lo] + th->h_xsize[lo] <= e - C::U) lo++;
+      fmax = std::max<int>(fmax, (int)(o - lo + 1));
+    }
+  }
+  P.tg = C::TG;
+  P.vr = (P.tg - 1 + fmax + 3) / 4 * 4;
+  if (P.vr > 32) return fail(AA_ERR_UNSUPPORTED, "stream: too many output rows finish per input batch (upsampling in H)");
+  const int64_t planes = P.lin.planes;
+  P.total_units = planes * n_strips * P.oH;
+  const size_t smem = sizeof(float) * ((size_t)P.vr * P.vw + (size_t)strip_ox * P.Kw) + sizeof(int) * 2 * (size_t)strip_ox;
+  if (smem > 200 * 1024) return fail(AA_ERR_UNSUPPORTED, "stream: shared memory plan too large");
+  AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0, sms = 0;
+  AA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NT, smem));
+  AA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  if (occ < 1) return fail(AA_ERR_UNSUPPORTED, "stream: kernel does not fit on an SM");
+  int64_t grid = (int64_t)occ * sms;
+  const int64_t min_units = 4;  // do not cut segments shorter than this many output rows
+  grid = std::max<int64_t>(1, std::min<int64_t>(grid, P.total_units / min_units));
+  kern<<<(unsigned)grid, C::NT, smem, stream>>>(P);
+  AA_LAUNCH_CHECK("aa_stream_kernel");
+  return AA_OK;
+}
+
+template <int A>
+int launch_A(SParams& P, int in_dtype, int vec, const AxisTables* th, const AxisTables* tw, int device, cudaStream_t stream) {
+  if (in_dtype == AA_F32) {
+    if (vec == 4) return launch_cfg<A, 4, float>(P, th, tw, device, stream);
+    if (vec == 2) return launch_cfg<A, 2, float>(P, th, tw, device, stream);
+    return launch_cfg<A, 1, float>(P, th, tw, device, stream);
+  }
+  if (vec == 8) return launch_cfg<A, 8, uint8_t>(P, th, tw, device, stream);
+  return launch_cfg<A, 4, uint8_t>(P, th, tw, device, stream);
+}
+
+}  // namespace
+
+int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout,
+                  AxisTables* th, AxisTables* tw, int64_t H, int64_t W, int64_t oH, int64_t oW,
+                  uint32_t flags, cudaStream_t stream) {
+  (void)flags;
+  if (in_dtype != AA_F32 && in_dtype != AA_U8) return fail(AA_ERR_UNSUPPORTED, "stream: input must be f32 or u8");
+  if (th->dtype != AA_F32 || tw->dtype != AA_F32) return fail(AA_ERR_UNSUPPORTED, "stream: f32 tables only");
+  if (th->kt_max > kMaxA) return fail(AA_ERR_UNSUPPORTED, "stream: too many output rows per input row (upsampling in H)");
+  if (oH >= (1 << 24) || W * lin.Ci >= (1ll << 30)) return fail(AA_ERR_UNSUPPORTED, "stream: size limits");
+  // widest vector the addresses allow: base pointer, plane strides and row stride must all be aligned
+  const int es = in_dtype == AA_F32 ? 4 : 1;
+  auto aligned = [&](int vec) {
+    const int64_t bytes = (int64_t)vec * es;
+    if (((uintptr_t)in) % bytes) return false;
+    if ((lin.stride_h % vec) || (lin.stride_n % vec) || (lin.Cp > 1 && lin.stride_p % vec)) return false;
+    return true;
+  };
+  int vec = 0;
+  if (in_dtype == AA_F32) { for (int v : {4, 2, 1}) if (aligned(v)) { vec = v; break; } }
+  else { for (int v : {8, 4}) if (aligned(v)) { vec = v; break; } }
+  if (!vec) return fail(AA_ERR_UNSUPPORTED, "stream: input rows are not sufficiently aligned");
+  const int A = th->kt_max <= 3 ? 3 : th->kt_max;
+  int rc = ensure_slot_tables(th, A, stream);
+  if (rc != AA_OK) return rc;
+
+  SParams P;
+  P.in = in; P.out = (float*)out; P.lin = lin; P.lout = lout; P.Ci = lin.Ci;
+  P.H = H; P.oH = oH; P.oW = oW;
+  P.slot_h = th->slot; P.RS = th->slot_RS;
+  P.xmin_h = th->xmin; P.xsize_h = th->xsize;
+  P.xmin_w = tw->xmin; P.xsize_w = tw->xsize; P.w_w = (const float*)tw->w; P.Kw = tw->K;
+  switch (A) {
+    case 3: return launch_A<3>(P, in_dtype, vec, th, tw, th->device, stream);
+    case 4: return launch_A<4>(P, in_dtype, vec, th, tw, th->device, stream);
+    case 5: return launch_A<5>(P, in_dtype, vec, th, tw, th->device, stream);
+    case 6: return launch_A<6>(P, in_dtype, vec, th, tw, th->device, stream);
+  }
+  return fail(AA_ERR_UNSUPPORTED, "stream: unsupported slot count");
+}
+
+}  // namespace aa

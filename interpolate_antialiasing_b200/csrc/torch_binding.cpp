@@ -1,0 +1,128 @@
+// torch_binding.cpp -- the reference's pybind operator boundary, re-hosted on the C ABI.
+//
+// Exports the same names with the same positional signatures as
+// /root/reference/step_two_dot_two/extension_interpolate.cpp:46-51
+//   linear_forward(input, output_size, align_corners)  -> Tensor      (:7-14)
+//   cubic_forward(input, output_size, align_corners)   -> Tensor      (:35-42)
+//   nearest_forward(input, output_size, align_corners) -> Tensor      (:26-33, box filter)
+//   linear_backward(grad_output, output_size, input_size, align_corners) -> Tensor   (:16-24)
+// plus what the reference stubs out (test.py:111-116): cubic_backward, nearest_backward, and
+// linear_backward_nonaa (the reference's literal, non-antialiased backward arithmetic).
+//
+// Semantics kept: output_size = (oH, oW); scale is always in/out (scale_factors {});
+// align_corners only changes the scale; 4-D input; empty batch allowed; memory format of the
+// result = input.suggest_memory_format() (aa_interpolation_impl.h:752) / grad_output's
+// (aa_interpolation_backward_impl.h:214); errors surface as RuntimeError.  Differences: tensors
+// must be CUDA tensors (there is NO CPU fallback), and uint8 inputs are accepted by
+// linear/cubic_forward with the caller's `.float()` (test.py:55,67) fused (result is float32).
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+#include <torch/extension.h>
+
+#include "aa_resize.h"
+
+namespace {
+
+int to_aa_dtype(at::ScalarType t) {
+  switch (t) {
+    case at::kByte: return AA_U8;
+    case at::kFloat: return AA_F32;
+    case at::kDouble: return AA_F64;
+    default: TORCH_CHECK(false, "\"upsample_generic_Nd\" not implemented for '", c10::toString(t), "'");
+  }
+}
+
+aa_tensor_desc make_desc(const at::Tensor& t) {
+  aa_tensor_desc d;
+  d.data = t.numel() ? t.data_ptr() : nullptr;
+  d.dtype = to_aa_dtype(t.scalar_type());
+  d.device = t.device().index();
+  d.n = t.size(0); d.c = t.size(1); d.h = t.size(2); d.w = t.size(3);
+  d.stride_n = t.stride(0); d.stride_c = t.stride(1); d.stride_h = t.stride(2); d.stride_w = t.stride(3);
+  return d;
+}
+
+// same checks and messages as at::native::upsample_2d_common_check (ATen/native/UpSample.h)
+void common_check(at::IntArrayRef input_size, at::IntArrayRef output_size) {
+  TORCH_CHECK(output_size.size() == 2, "It is expected output_size equals to 2, but got size ", output_size.size());
+  TORCH_CHECK(input_size.size() == 4, "It is expected input_size equals to 4, but got size ", input_size.size());
+  TORCH_CHECK(input_size[2] > 0 && input_size[3] > 0 && output_size[0] > 0 && output_size[1] > 0,
+              "Input and output sizes should be greater than 0, but got input (H: ", input_size[2], ", W: ", input_size[3],
+              ") output (H: ", output_size[0], ", W: ", output_size[1], ")");
+}
+
+at::Tensor forward_common(const at::Tensor& input, at::IntArrayRef output_size, bool align_corners, int filter, int64_t flags) {
+  TORCH_CHECK(input.is_cuda(), "aa_interp_b200: input must be a CUDA tensor (this build has no CPU fallback)");
+  common_check(input.sizes(), output_size);
+  // Allow for empty batch size but not other dimensions (aa_interpolation_impl.h:747-750)
+  TORCH_CHECK(input.numel() != 0 || c10::multiply_integers(input.sizes().begin() + 1, input.sizes().end()),
+              "Non-empty 4D data tensor expected but got a tensor with sizes ", input.sizes());
+  const auto fmt = input.suggest_memory_format();
+  const at::Tensor x = input.contiguous(fmt);
+  const auto out_dtype = x.scalar_type() == at::kDouble ? at::kDouble : at::kFloat;
+  to_aa_dtype(x.scalar_type());
+  at::Tensor out = at::empty({x.size(0), x.size(1), output_size[0], output_size[1]},
+                             x.options().dtype(out_dtype).memory_format(fmt));
+  c10::cuda::CUDAGuard guard(x.device());
+  auto stream = c10::cuda::getCurrentCUDAStream();
+  aa_tensor_desc di = make_desc(x), dd = make_desc(out);
+  const int rc = aa_resize_forward(&di, &dd, filter, align_corners ? 1 : 0, (uint32_t)flags, stream.stream());
+  TORCH_CHECK(rc == 0, "aa_resize_forward failed (", rc, "): ", aa_last_error());
+  return out;
+}
+
+at::Tensor backward_common(const at::Tensor& grad_output, at::IntArrayRef output_size, at::IntArrayRef input_size,
+                           bool align_corners, int filter, bool nonaa) {
+  TORCH_CHECK(grad_output.is_cuda(), "aa_interp_b200: grad_output must be a CUDA tensor (no CPU fallback)");
+  common_check(input_size, output_size);
+  // same checks as ti_upsample_bilinear2d_backward_cpu, aa_interpolation_backward_impl.h:201-212
+  TORCH_CHECK(grad_output.dim() == 4, "Expected grad_output to be a tensor of dimension 4 but got: dimension ", grad_output.dim());
+  const int64_t full[4] = {input_size[0], input_size[1], output_size[0], output_size[1]};
+  for (int i = 0; i < 4; ++i)
+    TORCH_CHECK(grad_output.size(i) == full[i], "Expected grad_output to have the same shape as output;", " output.size(", i,
+                ") = ", full[i], " but got grad_output.size(", i, ") = ", grad_output.size(i));
+  TORCH_CHECK(grad_output.scalar_type() == at::kFloat || grad_output.scalar_type() == at::kDouble,
+              "\"ti_upsample_bilinear2d_backward\" not implemented for '", c10::toString(grad_output.scalar_type()), "'");
+  const auto fmt = grad_output.suggest_memory_format();
+  const at::Tensor g = grad_output.contiguous(fmt);
+  at::Tensor gin = at::empty(input_size, g.options().memory_format(fmt));  // no zero_(): every element is written
+  c10::cuda::CUDAGuard guard(g.device());
+  auto stream = c10::cuda::getCurrentCUDAStream();
+  aa_tensor_desc dg = make_desc(g), di = make_desc(gin);
+  const int rc = nonaa ? aa_resize_backward_nonaa_bilinear(&dg, &di, align_corners ? 1 : 0, stream.stream())
+                       : aa_resize_backward(&dg, &di, filter, align_corners ? 1 : 0, 0u, stream.stream());
+  TORCH_CHECK(rc == 0, "aa_resize_backward failed (", rc, "): ", aa_last_error());
+  return gin;
+}
+
+at::Tensor linear_forward(const at::Tensor& i, at::IntArrayRef o, bool a) { return forward_common(i, o, a, AA_FILTER_TRIANGLE, 0); }
+at::Tensor cubic_forward(const at::Tensor& i, at::IntArrayRef o, bool a) { return forward_common(i, o, a, AA_FILTER_CUBIC, 0); }
+at::Tensor nearest_forward(const at::Tensor& i, at::IntArrayRef o, bool a) { return forward_common(i, o, a, AA_FILTER_BOX, 0); }
+at::Tensor forward_with_flags(const at::Tensor& i, at::IntArrayRef o, bool a, int64_t filter, int64_t flags) {
+  return forward_common(i, o, a, (int)filter, flags);
+}
+at::Tensor linear_backward(const at::Tensor& g, at::IntArrayRef o, at::IntArrayRef i, bool a) {
+  return backward_common(g, o, i, a, AA_FILTER_TRIANGLE, false);
+}
+at::Tensor cubic_backward(const at::Tensor& g, at::IntArrayRef o, at::IntArrayRef i, bool a) {
+  return backward_common(g, o, i, a, AA_FILTER_CUBIC, false);
+}
+at::Tensor nearest_backward(const at::Tensor& g, at::IntArrayRef o, at::IntArrayRef i, bool a) {
+  return backward_common(g, o, i, a, AA_FILTER_BOX, false);
+}
+at::Tensor linear_backward_nonaa(const at::Tensor& g, at::IntArrayRef o, at::IntArrayRef i, bool a) {
+  return backward_common(g, o, i, a, AA_FILTER_TRIANGLE, true);
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("linear_forward", &linear_forward, "Anti-Aliased Linear Interpolation forward (sm_100a)");
+  m.def("nearest_forward", &nearest_forward, "Anti-Aliased box ('nearest') Interpolation forward (sm_100a)");
+  m.def("cubic_forward", &cubic_forward, "Anti-Aliased Cubic Interpolation forward (sm_100a)");
+  m.def("linear_backward", &linear_backward, "Anti-Aliased Linear Interpolation backward: true adjoint (sm_100a)");
+  m.def("cubic_backward", &cubic_backward, "Anti-Aliased Cubic Interpolation backward: true adjoint (sm_100a)");
+  m.def("nearest_backward", &nearest_backward, "Anti-Aliased box Interpolation backward: true adjoint (sm_100a)");
+  m.def("linear_backward_nonaa", &linear_backward_nonaa, "The reference's literal (non-antialiased) linear backward");
+  m.def("forward_with_flags", &forward_with_flags, "forward(input, output_size, align_corners, filter, AA_FLAG_*)");
+}
