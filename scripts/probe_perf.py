@@ -1,0 +1,69 @@
+"""Quick device-time probe of the named configs (not the bench contract; used while tuning)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from interpolate_antialiasing_b200 import capi
+
+dev = torch.device("cuda", 0)
+PEAK = 6531.6
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in ev:
+        a.record(); fn(); b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in ev)
+    return ts[len(ts) // 2], ts[0]
+
+
+def run(name, x, osize, mode, flags, bytes_):
+    try:
+        out = capi.resize_forward(x, osize, mode, False, flags)
+        med, best = timeit(lambda: capi.resize_forward(x, osize, mode, False, flags, out=out))
+        print(f"{name:58s} med {med*1e3:9.1f} us  best {best*1e3:9.1f} us  {bytes_/med/1e6:8.1f} GB/s  {bytes_/med/1e6/PEAK*100:5.1f}% of peak", flush=True)
+    except capi.AAError as e:
+        print(f"{name:58s} ERROR {e}", flush=True)
+
+
+which = sys.argv[1:] or ["cfg2", "cfg3", "cfg1", "cfg4", "torch"]
+g = torch.Generator(device="cuda").manual_seed(0)
+if "cfg2" in which:
+    N = 64
+    x = (torch.rand((N, 3, 1080, 1920), generator=g, device=dev) * 255).contiguous(memory_format=torch.channels_last)
+    b = N * 3 * (1080 * 1920 + 224 * 224) * 4
+    run("cfg2/4 fp32 CL 64x3x1080x1920->224 bilinear STREAM", x, (224, 224), "linear", capi.FLAG_FORCE_STREAM, b)
+    run("cfg2/4 same GENERAL", x, (224, 224), "linear", capi.FLAG_FORCE_GENERAL, b)
+    xcf = x.contiguous()
+    run("cfg2/4 fp32 CF STREAM", xcf, (224, 224), "linear", capi.FLAG_FORCE_STREAM, b)
+    if "torch" in which:
+        med, best = timeit(lambda: torch.nn.functional.interpolate(x, size=(224, 224), mode="bilinear", antialias=True))
+        print(f"{'torch F.interpolate(antialias=True) CL (incumbent)':58s} med {med*1e3:9.1f} us  {b/med/1e6:8.1f} GB/s")
+        med, best = timeit(lambda: torch.nn.functional.interpolate(xcf, size=(224, 224), mode="bilinear", antialias=True))
+        print(f"{'torch F.interpolate(antialias=True) CF (incumbent)':58s} med {med*1e3:9.1f} us  {b/med/1e6:8.1f} GB/s")
+    del x, xcf
+if "cfg3" in which:
+    N = 32
+    x = torch.randint(0, 256, (N, 3, 2160, 3840), generator=g, device=dev, dtype=torch.uint8)
+    b = N * 3 * (2160 * 3840 * 1 + 512 * 512 * 4)
+    run("cfg3/4 u8 CF 32x3x2160x3840->512 bicubic STREAM", x, (512, 512), "cubic", capi.FLAG_FORCE_STREAM, b)
+    xf = x[:8].float()
+    b2 = 8 * 3 * (2160 * 3840 * 4 + 512 * 512 * 4)
+    run("cfg3 fp32 variant 8 imgs bicubic STREAM", xf, (512, 512), "cubic", capi.FLAG_FORCE_STREAM, b2)
+    del x, xf
+if "cfg1" in which:
+    x = torch.rand((1, 3, 438, 906), generator=g, device=dev) * 255
+    b = 3 * (438 * 906 + 196 * 320) * 4
+    run("cfg1 fp32 CF 1x3x438x906->196x320 bilinear AUTO", x, (196, 320), "linear", capi.FLAG_AUTO, b)
+    run("cfg1 same GENERAL", x, (196, 320), "linear", capi.FLAG_FORCE_GENERAL, b)
+if "cfg4" in which:
+    go = torch.rand((64, 3, 128, 128), generator=g, device=dev)
+    b = 64 * 3 * (128 * 128 + 512 * 512) * 4
+    gi = capi.resize_backward(go, (64, 3, 512, 512), "linear")
+    med, best = timeit(lambda: capi.resize_backward(go, (64, 3, 512, 512), "linear"))
+    print(f"{'cfg4 backward bilinear 64x3x128^2 -> 512^2':58s} med {med*1e3:9.1f} us  best {best*1e3:9.1f} us  {b/med/1e6:8.1f} GB/s  {b/med/1e6/PEAK*100:5.1f}% of peak")
+    x = torch.rand((64, 3, 512, 512), generator=g, device=dev)
+    run("cfg4 forward 64x3x512^2->128^2 bilinear AUTO", x, (128, 128), "linear", capi.FLAG_AUTO, b)

@@ -1,0 +1,100 @@
+"""K3 parity: gather-form adjoint through the C ABI / torch extension.
+fp32 vs the adjoint oracle within 1e-5 rel / 1e-3 abs; fp64 gradcheck of the forward/backward pair."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import aa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def test_adjoint_vs_oracle(cuda):
+    from interpolate_antialiasing_b200 import capi
+    g = torch.Generator().manual_seed(2)
+    shapes = [((2, 3, 37, 53), (11, 17)), ((2, 4, 16, 20), (33, 47)), ((1, 1, 40, 30), (13, 64)), ((3, 2, 9, 9), (9, 9)),
+              ((1, 3, 30, 50), (1, 1)), ((1, 2, 1, 1), (4, 5)), ((2, 3, 128, 128), (32, 32))]
+    for shp, osz in shapes:
+        for mode in ("linear", "cubic", "nearest"):
+            for align in (False, True):
+                for tdt in (torch.float32, torch.float64):
+                    for cl in (False, True):
+                        go = torch.rand(shp[:2] + osz, generator=g, dtype=tdt)
+                        want = O.backward_adjoint(go.numpy(), shp, mode, align)
+                        gc = go.to(cuda)
+                        if cl:
+                            gc = gc.contiguous(memory_format=torch.channels_last)
+                        got = capi.resize_backward(gc, shp, mode, align)
+                        torch.cuda.synchronize()
+                        tol = 1e-4 if tdt == torch.float32 else 1e-12
+                        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=tol)
+
+
+def test_nonaa_backward_bit_exact_vs_reference_golden(cuda, golden):
+    """The reference's exported linear_backward (non-AA) reproduced bit for bit (regression target)."""
+    from interpolate_antialiasing_b200 import capi
+    for i in range(int(golden["n_cases"])):
+        x = golden[f"case{i}_x"]
+        go = torch.from_numpy(golden[f"case{i}_gout"]).to(cuda)
+        for align in (0, 1):
+            got = capi.resize_backward(go, x.shape, "linear", bool(align), nonaa=True)
+            torch.cuda.synchronize()
+            assert np.array_equal(got.cpu().numpy(), golden[f"case{i}_linbwd_{align}"]), (i, align)
+
+
+def test_gradcheck_fp64(cuda):
+    """north_star: backward validated by gradcheck in fp64 (small shapes: down, up, mixed; both filters)."""
+    import interpolate_antialiasing_b200 as aa
+    torch.manual_seed(0)
+    for shp, osz in [((1, 2, 12, 16), (5, 6)), ((1, 2, 6, 8), (12, 16)), ((2, 1, 10, 7), (4, 15))]:
+        for mode in ("bilinear", "bicubic", "nearest"):
+            for align in (False, True):
+                x = torch.rand(shp, dtype=torch.float64, device=cuda, requires_grad=True)
+                assert torch.autograd.gradcheck(lambda t: aa.aa_resize(t, osz, mode, align), (x,), eps=1e-6, atol=1e-6, rtol=1e-6,
+                                                check_batched_grad=False, nondet_tol=0.0)
+
+
+def test_cfg4_full_size_inner_product_and_torch(cuda):
+    """cfg4: grad of bilinear AA [64,3,512,512] -> [128,128].  <A x, g> == <x, A^T g> ties the backward
+    kernel to the forward kernel at full size; torch's own CUDA AA backward is a second opinion."""
+    import interpolate_antialiasing_b200 as aa
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand((64, 3, 512, 512), generator=gen, device=cuda)
+    go = torch.rand((64, 3, 128, 128), generator=gen, device=cuda)
+    y = aa.linear_forward(x, (128, 128), False)
+    gi = aa.linear_backward(go, (128, 128), x.shape, False)
+    assert gi.shape == x.shape
+    lhs = (y.double() * go.double()).sum().item()
+    rhs = (x.double() * gi.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * abs(lhs)
+    xt = x.clone().requires_grad_(True)
+    yt = torch.nn.functional.interpolate(xt, size=(128, 128), mode="bilinear", antialias=True, align_corners=False)
+    (gt,) = torch.autograd.grad(yt, xt, go)
+    assert (gt - gi).abs().max().item() < 1e-5
+    # one image against the adjoint oracle
+    want = O.backward_adjoint(go[:1].cpu().numpy(), (1, 3, 512, 512), "linear", False)
+    np.testing.assert_allclose(gi[:1].cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+
+
+def test_extension_matches_reference_api(cuda, golden):
+    """The torch extension keeps the reference's names/positional signatures and error behaviour."""
+    import interpolate_antialiasing_b200 as aa
+    m = aa.load()
+    for name in ("linear_forward", "cubic_forward", "nearest_forward", "linear_backward"):
+        assert hasattr(m, name)
+    x = torch.from_numpy(golden["case0_x"]).to(cuda)
+    y = m.linear_forward(x, (11, 17), False)
+    assert np.allclose(y.cpu().numpy(), golden["case0_linear_0"], rtol=1e-5, atol=1e-3)
+    ycl = m.cubic_forward(x.contiguous(memory_format=torch.channels_last), (11, 17), False)
+    assert ycl.is_contiguous(memory_format=torch.channels_last)
+    with pytest.raises(RuntimeError):
+        m.linear_forward(x[0], (11, 17), False)  # 3-D input
+    with pytest.raises(RuntimeError):
+        m.linear_forward(x.cpu(), (11, 17), False)  # no CPU fallback
+    with pytest.raises(RuntimeError):
+        m.linear_backward(y, (11, 18), list(x.shape), False)  # shape mismatch message path
+    with pytest.raises(RuntimeError):
+        m.linear_forward(x.half(), (11, 17), False)
+    # uint8 in -> float32 out (fused cast)
+    yu = m.linear_forward(x.byte(), (11, 17), False)
+    assert yu.dtype == torch.float32

@@ -1,0 +1,96 @@
+"""CPU-only checks of the boundary: the C-ABI library loads and exports every symbol the header
+declares, host-only queries agree with the oracle, and argument errors come back as status codes
+(no compute call is made here: there is no GPU in the build container and no CPU fallback)."""
+import ctypes
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+from oracle import aa_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "aa_resize.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(aa_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    from interpolate_antialiasing_b200 import capi
+    L = capi.lib()
+    names = _declared_functions()
+    assert len(names) >= 11
+    assert set(names) == set(capi.EXPORTS)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/aa_resize.h but not exported"
+    assert L.aa_abi_version() == 1
+
+
+def test_no_oracle_in_product_path():
+    """The product must not route through the oracle or any CPU fallback."""
+    pkg = os.path.join(ROOT, "interpolate_antialiasing_b200")
+    for dp, _, fs in os.walk(pkg):
+        if "_build" in dp:
+            continue
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "aa_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_interp_size_matches_oracle():
+    from interpolate_antialiasing_b200 import capi
+    rnd = random.Random(9)
+    for _ in range(2000):
+        a, b = rnd.randint(1, 6000), rnd.randint(1, 6000)
+        mode = rnd.choice(["linear", "cubic", "nearest"])
+        align = rnd.random() < 0.5
+        assert capi.interp_size(a, b, mode, align, capi.F32) == O.interp_size(a, b, mode, align, np.float32)
+        assert capi.interp_size(a, b, mode, align, capi.F64) == O.interp_size(a, b, mode, align, np.float64)
+
+
+def test_argument_errors_are_status_codes():
+    from interpolate_antialiasing_b200 import capi
+    L = capi.lib()
+    k = ctypes.c_int32(0)
+    assert L.aa_interp_size(0, 10, 1, 0, 1, ctypes.byref(k)) == -1
+    assert b"bad arguments" in L.aa_last_error()
+    assert L.aa_interp_size(10, 10, 9, 0, 1, ctypes.byref(k)) == -1
+    d = capi.TensorDesc(None, capi.F32, 0, 1, 3, 0, 8, 0, 0, 0, 0)   # h == 0
+    o = capi.TensorDesc(None, capi.F32, 0, 1, 3, 4, 4, 48, 16, 4, 1)
+    assert L.aa_resize_forward(ctypes.byref(d), ctypes.byref(o), 1, 0, 0, None) == -1
+    assert b"Non-empty 4D data tensor expected" in L.aa_last_error()
+    assert L.aa_resize_forward(None, ctypes.byref(o), 1, 0, 0, None) == -1
+    d = capi.TensorDesc(None, capi.F32, 0, 0, 3, 8, 8, 192, 64, 8, 1)   # empty batch: OK, no device touched
+    o = capi.TensorDesc(None, capi.F32, 0, 0, 3, 4, 4, 48, 16, 4, 1)
+    assert L.aa_resize_forward(ctypes.byref(d), ctypes.byref(o), 1, 0, 0, None) == 0
+    assert L.aa_resize_backward(ctypes.byref(o), ctypes.byref(d), 1, 0, 0, None) == 0
+    o = capi.TensorDesc(None, capi.F64, 0, 0, 3, 4, 4, 48, 16, 4, 1)    # dtype mismatch
+    assert L.aa_resize_forward(ctypes.byref(d), ctypes.byref(o), 1, 0, 0, None) == -1
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    import interpolate_antialiasing_b200 as aa
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        aa.linear_forward(torch.rand(1, 3, 8, 8), (4, 4), False)
+    # the C ABI itself reports a CUDA error rather than computing on the host
+    x = torch.rand(1, 3, 8, 8); y = torch.empty(1, 3, 4, 4)
+    di, do = aa.capi.desc(x, 0), aa.capi.desc(y, 0)
+    rc = aa.capi.lib().aa_resize_forward(ctypes.byref(di), ctypes.byref(do), 1, 0, 0, None)
+    assert rc in (-3, -4) and b"CUDA error" in aa.capi.lib().aa_last_error()
+
+
+def test_extension_exports_reference_names():
+    import interpolate_antialiasing_b200 as aa
+    m = aa.load()
+    # /root/reference/step_two_dot_two/extension_interpolate.cpp:46-51
+    for name in ("linear_forward", "nearest_forward", "cubic_forward", "linear_backward"):
+        assert callable(getattr(m, name))

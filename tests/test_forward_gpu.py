@@ -1,0 +1,200 @@
+"""K2 parity: forward through the C ABI against the oracle / golden fixtures.
+
+Tolerances (BASELINE.json north_star): fp32 within 1e-5 relative / 1e-3 absolute on a [0,255]
+scale (checked as |got-want| <= 1e-3 + 1e-5*|want|); uint8-rounded outputs within 1 LSB.
+The general path (AA_FLAG_FORCE_GENERAL: H pass then V pass, no FMA) is held to BIT-EXACT."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import aa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ATOL, RTOL = 1e-3, 1e-5
+MODES = ["linear", "cubic", "nearest"]
+SIZES = [(320, 196), (460, 220), (120, 96), (1200, 196), (120, 1200)]  # PIL (w, h), reference test.py:15-21
+
+
+def _close(got, want):
+    got = got.astype(np.float64); want = want.astype(np.float64)
+    err = np.abs(got - want)
+    assert np.all(err <= ATOL + RTOL * np.abs(want)), f"max abs err {err.max():.3e}"
+    return err.max()
+
+
+def _run(capi, x, osize, mode, align, flags):
+    y = capi.resize_forward(x, osize, mode, align, flags)
+    torch.cuda.synchronize()
+    return y
+
+
+def test_small_cases_general_bit_exact(cuda, golden):
+    from interpolate_antialiasing_b200 import capi
+    for i in range(int(golden["n_cases"])):
+        xn = golden[f"case{i}_x"]
+        osize = tuple(int(v) for v in golden[f"case{i}_osize"])
+        for cl in (False, True):
+            x = torch.from_numpy(xn).to(cuda)
+            if cl:
+                x = x.contiguous(memory_format=torch.channels_last)
+            for mode in MODES:
+                for align in (0, 1):
+                    y = _run(capi, x, osize, mode, bool(align), capi.FLAG_FORCE_GENERAL)
+                    assert y.is_contiguous(memory_format=torch.channels_last if cl else torch.contiguous_format) or min(y.shape) == 1
+                    assert np.array_equal(y.cpu().numpy(), golden[f"case{i}_{mode}_{align}"]), (i, cl, mode, align)
+
+
+def test_small_cases_auto_within_tolerance(cuda, golden):
+    from interpolate_antialiasing_b200 import capi
+    for i in range(int(golden["n_cases"])):
+        xn = golden[f"case{i}_x"]
+        if xn.dtype != np.float32:
+            continue
+        osize = tuple(int(v) for v in golden[f"case{i}_osize"])
+        for cl in (False, True):
+            x = torch.from_numpy(xn).to(cuda)
+            if cl:
+                x = x.contiguous(memory_format=torch.channels_last)
+            for mode in MODES:
+                for align in (0, 1):
+                    y = _run(capi, x, osize, mode, bool(align), capi.FLAG_AUTO)
+                    _close(y.cpu().numpy(), golden[f"case{i}_{mode}_{align}"])
+
+
+@pytest.mark.parametrize("flags_name", ["FLAG_FORCE_GENERAL", "FLAG_FORCE_STREAM", "FLAG_AUTO"])
+def test_photo_all_sizes(cuda, photo, golden, flags_name):
+    """cfg1 and the reference's 5 test sizes on its own fixture image, f32 and fused-uint8 input."""
+    from interpolate_antialiasing_b200 import capi
+    flags = getattr(capi, flags_name)
+    xu8 = torch.from_numpy(photo.transpose(2, 0, 1)[None].copy()).to(cuda)
+    xf = xu8.float()
+    want_cache = {}
+    for (w, h) in SIZES:
+        for mode in MODES:
+            want = O.forward(xf.cpu().numpy(), (h, w), mode)
+            want_cache[(w, h, mode)] = want
+            for x in (xf, xu8, xf.contiguous(memory_format=torch.channels_last), xu8.contiguous(memory_format=torch.channels_last)):
+                try:
+                    y = _run(capi, x, (h, w), mode, False, flags)
+                except capi.AAError as e:
+                    if flags == capi.FLAG_FORCE_STREAM and "-2" in str(e):
+                        continue  # stream path legitimately ineligible (upsampling in H / alignment)
+                    raise
+                got = y.cpu().numpy()
+                if flags == capi.FLAG_FORCE_GENERAL:
+                    assert np.array_equal(got, want), (w, h, mode)
+                else:
+                    _close(got, want)
+    # the reference's committed golden PNG: bilinear 320x196, .byte() truncation; general path is bit-exact
+    y = _run(capi, xf, (196, 320), "linear", False, capi.FLAG_FORCE_GENERAL)
+    assert np.array_equal(y[0].byte().permute(1, 2, 0).cpu().numpy(), golden["png_320x196"])
+    # streaming path: within 1 LSB of it after the same truncation
+    y = _run(capi, xf, (196, 320), "linear", False, capi.FLAG_AUTO)
+    d = np.abs(y[0].byte().permute(1, 2, 0).cpu().numpy().astype(np.int32) - golden["png_320x196"].astype(np.int32))
+    assert d.max() <= 1
+
+
+def test_photo_vs_pil(cuda, photo):
+    """Reference acceptance check test.py:360-379: bilinear MAE<1 & MaxAbsE<=1; bicubic MAE<1 & MaxAbsE<20."""
+    from PIL import Image
+    from interpolate_antialiasing_b200 import capi
+    img = Image.fromarray(photo)
+    xu8 = torch.from_numpy(photo.transpose(2, 0, 1)[None].copy()).to(cuda)
+    for (w, h) in SIZES:
+        for mode, resample, max_tol in (("linear", Image.BILINEAR, 1.0 + 1e-5), ("cubic", Image.BICUBIC, 20.0)):
+            pil = np.asarray(img.resize((w, h), resample=resample)).transpose(2, 0, 1).astype(np.float32)
+            y = _run(capi, xu8, (h, w), mode, False, capi.FLAG_AUTO)[0]
+            if mode == "cubic":
+                y = y.clamp(0, 255)
+            y = y.byte().float().cpu().numpy()
+            assert np.abs(y - pil).mean() < 1.0
+            assert np.abs(y - pil).max() < max_tol
+
+
+@pytest.mark.parametrize("C", [1, 3, 4])
+@pytest.mark.parametrize("cl", [False, True])
+def test_scale_sweep_medium(cuda, C, cl):
+    """cfg5 at oracle-sized shapes: scale 0.125x..2x in both axes incl. mixed up/down, both filters."""
+    from interpolate_antialiasing_b200 import capi
+    g = torch.Generator().manual_seed(C * 2 + cl)
+    H, W = 96, 128
+    x = (torch.rand((2, C, H, W), generator=g) * 255)
+    xc = x.to(cuda)
+    if cl:
+        xc = xc.contiguous(memory_format=torch.channels_last)
+    for sh, sw in [(0.125, 0.125), (0.25, 0.5), (0.333, 0.333), (0.5, 0.25), (0.75, 0.75), (1, 1), (1.5, 1.5), (2, 2), (0.25, 2), (2, 0.25), (0.6, 1.3)]:
+        osize = (max(1, round(H * sh)), max(1, round(W * sw)))
+        for mode in ("linear", "cubic"):
+            want = O.forward(x.numpy(), osize, mode, False)
+            y = _run(capi, xc, osize, mode, False, capi.FLAG_AUTO)
+            _close(y.cpu().numpy(), want)
+            y = _run(capi, xc, osize, mode, False, capi.FLAG_FORCE_GENERAL)
+            assert np.array_equal(y.cpu().numpy(), want), (sh, sw, mode)
+
+
+def test_named_config_slices(cuda):
+    """One-image slices of cfg2 (fp32 channels_last bilinear 1080x1920->224x224) and cfg3
+    (uint8 channels_first bicubic 2160x3840->512x512) against the oracle."""
+    from interpolate_antialiasing_b200 import capi
+    g = torch.Generator().manual_seed(0)
+    x = (torch.rand((2, 3, 1080, 1920), generator=g) * 255)
+    want = O.forward(x.numpy(), (224, 224), "linear", False)
+    y = _run(capi, x.to(cuda).contiguous(memory_format=torch.channels_last), (224, 224), "linear", False, capi.FLAG_AUTO)
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    _close(y.cpu().numpy(), want)
+    xu = torch.randint(0, 256, (1, 3, 2160, 3840), generator=g, dtype=torch.uint8)
+    want = O.forward(xu.float().numpy(), (512, 512), "cubic", False)
+    y = _run(capi, xu.to(cuda), (512, 512), "cubic", False, capi.FLAG_AUTO)
+    e = _close(y.cpu().numpy(), want)
+    # uint8-rounded (clamp + cast as the reference's caller does, test.py:71-75) within 1 LSB
+    a = np.clip(y.cpu().numpy(), 0, 255).astype(np.uint8).astype(np.int32)
+    b = np.clip(want, 0, 255).astype(np.uint8).astype(np.int32)
+    assert np.abs(a - b).max() <= 1, e
+
+
+def test_full_size_properties(cuda):
+    """Size-independent properties at BASELINE sizes (a 16-image slab of cfg2; cfg3 full per-image size):
+    constants are preserved (weights sum to 1), the op is linear, batch elements are independent,
+    and channels_first / channels_last agree."""
+    from interpolate_antialiasing_b200 import capi
+    g = torch.Generator(device="cuda").manual_seed(1)
+    N = 16
+    x = (torch.rand((N, 3, 1080, 1920), generator=g, device=cuda) * 255).contiguous(memory_format=torch.channels_last)
+    y = _run(capi, x, (224, 224), "linear", False, capi.FLAG_AUTO)
+    ones = torch.full_like(x, 37.0)
+    yo = _run(capi, ones, (224, 224), "linear", False, capi.FLAG_AUTO)
+    assert (yo - 37.0).abs().max().item() < 1e-3
+    y2 = _run(capi, x * 0.5 + ones, (224, 224), "linear", False, capi.FLAG_AUTO)
+    assert (y2 - (0.5 * y + yo)).abs().max().item() < 1e-3
+    y3 = _run(capi, x[5:6], (224, 224), "linear", False, capi.FLAG_AUTO)
+    assert torch.equal(y3, y[5:6])
+    ycf = _run(capi, x.contiguous(), (224, 224), "linear", False, capi.FLAG_AUTO)
+    assert (ycf - y).abs().max().item() < 1e-3
+    # one image against the oracle
+    _close(y[3:4].cpu().numpy(), O.forward(x[3:4].cpu().numpy(), (224, 224), "linear", False))
+
+
+def test_edge_cases(cuda):
+    from interpolate_antialiasing_b200 import capi
+    # empty batch is allowed (aa_interpolation_impl.h:747-750)
+    x = torch.empty((0, 3, 8, 8), device=cuda)
+    y = capi.resize_forward(x, (4, 4), "linear")
+    assert y.shape == (0, 3, 4, 4)
+    # 1x1 in / 1x1 out / identity
+    g = torch.Generator().manual_seed(4)
+    for shp, osz in [((1, 2, 1, 1), (4, 5)), ((1, 3, 30, 50), (1, 1)), ((2, 2, 9, 9), (9, 9)), ((1, 1, 1, 37), (1, 5)), ((1, 1, 37, 1), (5, 1))]:
+        x = torch.rand(shp, generator=g) * 255
+        for mode in MODES:
+            want = O.forward(x.numpy(), osz, mode, False)
+            y = _run(capi, x.to(cuda), osz, mode, False, capi.FLAG_AUTO)
+            _close(y.cpu().numpy(), want)
+    # batch slice (stride_n != c*h*w) is read in place
+    xb = (torch.rand((6, 3, 40, 48), generator=g) * 255).to(cuda)
+    y = _run(capi, xb[1:5:2], (10, 12), "linear", False, capi.FLAG_AUTO)
+    _close(y.cpu().numpy(), O.forward(xb[1:5:2].cpu().numpy(), (10, 12), "linear", False))
+    # bad arguments surface as errors, not crashes
+    with pytest.raises(capi.AAError):
+        capi.resize_forward(torch.rand((1, 3, 8, 8), device=cuda), (4, 4), 7)
+    with pytest.raises(capi.AAError):  # non-NCHW/NHWC strides
+        capi.resize_forward(torch.rand((1, 3, 8, 16), device=cuda)[:, :, :, ::2], (4, 4), "linear")
