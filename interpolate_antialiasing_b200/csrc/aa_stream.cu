@@ -9,9 +9,10 @@
 //   * A plane row is a flat array of W*Ci elements (Ci = C for channels_last, 1 for channels_first),
 //     so the VERTICAL filter is layout-agnostic: thread t owns VEC consecutive flat elements and
 //     streams down the rows with 128-bit coalesced loads.  Each input row contributes to at most A
-//     output rows (A = 3 bilinear, 5 bicubic when downsampling), so the thread keeps A rotating
-//     accumulators per element: slot (oy % A) collects output row oy.  The per-row record
-//     {w[slot 0..A), first_flush_oy | nflush<<24} is warp-uniform (one 16/32-byte broadcast load).
+//     output rows (A = 3 bilinear, 5 bicubic when downsampling), so the thread keeps A
+//     accumulators per element, ordered by age: acc[k] collects the k-th oldest open output row.
+//     The per-row record {wT[y][0..A), first_flush_oy | nflush<<24} is warp-uniform (one 16/32-byte
+//     broadcast load).
 //   * When an output row's window ends, its accumulator (one vertically-filtered row, still at full
 //     input width) is flushed to shared memory.  Every G flushed rows the CTA runs the HORIZONTAL
 //     filter as a gather over the shared-memory rows (weights staged in shared memory, each weight
@@ -98,25 +99,6 @@ template <> struct VLoad<uint8_t, 4> {
   }
 };
 
-template <int A> struct Rec { float w[A]; int packed; };
-
-template <int A>
-__device__ __forceinline__ Rec<A> load_rec(const float* __restrict__ slot, int RS, int64_t y) {
-  Rec<A> r;
-  const float4* p = reinterpret_cast<const float4*>(slot + y * RS);
-  constexpr int NW = (A + 1 + 3) / 4;
-  float tmp[NW * 4];
-#pragma unroll
-  for (int i = 0; i < NW; i++) {
-    const float4 q = __ldg(p + i);
-    tmp[4 * i] = q.x; tmp[4 * i + 1] = q.y; tmp[4 * i + 2] = q.z; tmp[4 * i + 3] = q.w;
-  }
-#pragma unroll
-  for (int a = 0; a < A; a++) r.w[a] = tmp[a];
-  r.packed = __float_as_int(tmp[A]);
-  return r;
-}
-
 template <int VEC> __device__ __forceinline__ void store_vec(float* dst, const float* a) {
   if constexpr (VEC % 4 == 0) {
 #pragma unroll
@@ -134,12 +116,14 @@ template <int VEC> __device__ __forceinline__ void store_vec(float* dst, const f
 // VEC   flat elements per thread per row
 // NT    threads per CTA
 // U     input rows in flight per thread
+// MINB  CTAs per SM the register allocation must allow
 // Shared memory holds up to P.vr vertically-filtered rows; the horizontal phase runs at the end of a
 // U-row batch once at least P.tg rows are buffered (host guarantees tg - 1 + max flushes per batch <= vr).
-template <int A, int VEC, typename in_t, int NT, int U>
-__global__ void __launch_bounds__(NT) aa_stream_kernel(const SParams P) {
+template <int A, int VEC, typename in_t, int NT, int U, int MINB>
+__global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
   extern __shared__ __align__(16) float smem[];
   constexpr int RPT = 4;  // rows per thread in the horizontal phase
+  constexpr int RS4 = (A + 1 + 3) / 4;  // float4 per slot record
   float* Vs = smem;                                  // [vr][vw]
   float* Ws = Vs + (size_t)P.vr * P.vw;              // [strip_ox][Kw]
   int* sxmin = reinterpret_cast<int*>(Ws + (size_t)P.strip_ox * P.Kw);  // [strip_ox]
@@ -148,6 +132,8 @@ __global__ void __launch_bounds__(NT) aa_stream_kernel(const SParams P) {
   const int t = threadIdx.x;
   const int Ci = P.Ci;
   const int64_t oH = P.oH;
+  const int64_t stride_h = P.lin.stride_h;
+  const int vw = P.vw;
   const int64_t u_begin = P.total_units * (int64_t)blockIdx.x / gridDim.x;
   const int64_t u_end = P.total_units * (int64_t)(blockIdx.x + 1) / gridDim.x;
   int cur_strip = -1;
@@ -172,13 +158,16 @@ __global__ void __launch_bounds__(NT) aa_stream_kernel(const SParams P) {
     }
     const int fl0 = (sxmin[0] * Ci) & ~(VEC - 1);                            // first flat element of the strip
     const int fl_end = (sxmin[ox1 - ox0 - 1] + sxsize[ox1 - ox0 - 1]) * Ci;  // one past the last
-    const int fmy = fl0 + VEC * t;
-    const bool valid = fmy < fl_end;
-    const in_t* ip = (const in_t*)P.in + (plane / P.lin.Cp) * P.lin.stride_n + (plane % P.lin.Cp) * P.lin.stride_p + fmy;
-    float* op = P.out + (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p + (int64_t)ox0 * Ci;
+    const bool valid = fl0 + VEC * t < fl_end;
+    // threads beyond the strip re-read its first vector (a legal address) and never store
+    const int fmy = valid ? fl0 + VEC * t : fl0;
     const int64_t yA = __ldg(P.xmin_h + oyA);
     const int64_t yB = (int64_t)__ldg(P.xmin_h + oyB - 1) + __ldg(P.xsize_h + oyB - 1);
+    const in_t* ip = (const in_t*)P.in + (plane / P.lin.Cp) * P.lin.stride_n + (plane % P.lin.Cp) * P.lin.stride_p + fmy + yA * stride_h;
+    const float4* rp = reinterpret_cast<const float4*>(P.slot_h) + yA * RS4;
+    float* op = P.out + (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p + (int64_t)ox0 * Ci;
     const int nof = (ox1 - ox0) * Ci;
+    float* vdst = Vs + VEC * t;
 
     float acc[A][VEC];
 #pragma unroll
@@ -188,83 +177,92 @@ __global__ void __launch_bounds__(NT) aa_stream_kernel(const SParams P) {
     int gbase = oyA;  // output row held in Vs[0]
     int cnt = 0;      // rows buffered in Vs
 
-    for (int64_t y = yA; y < yB; y += U) {
+    // one input row: A FMAs per element with warp-uniform weights; acc[k] belongs to the k-th oldest
+    // open output row.  When rows finish (rarely: once per scale_h rows) the oldest accumulators are
+    // stored to shared memory and the rest shift down.
+    auto row = [&](const float (&v)[VEC], const float4 (&rq)[RS4]) {
+      const float* rw = reinterpret_cast<const float*>(rq);
+#pragma unroll
+      for (int a = 0; a < A; a++)
+#pragma unroll
+        for (int e = 0; e < VEC; e++) acc[a][e] = fmaf(rw[a], v[e], acc[a][e]);
+      const int packed = __float_as_int(rw[A]);
+      if (packed >> 24) {
+        const int nfl = packed >> 24;
+        int o = packed & 0xffffff;
+#pragma unroll 1
+        for (int k = 0; k < nfl; k++, o++) {
+          if (o >= oyA && o < oyB) {
+            if (valid) store_vec<VEC>(vdst + (size_t)cnt * vw, acc[0]);
+            cnt++;
+          }
+#pragma unroll
+          for (int a = 0; a + 1 < A; a++)
+#pragma unroll
+            for (int e = 0; e < VEC; e++) acc[a][e] = acc[a + 1][e];
+#pragma unroll
+          for (int e = 0; e < VEC; e++) acc[A - 1][e] = 0.f;
+        }
+      }
+    };
+    // horizontal filter over the buffered rows [gbase, gbase+cnt)
+    auto hphase = [&]() {
+      __syncthreads();
+      const int nrg = (cnt + RPT - 1) / RPT;
+      for (int item = t; item < nof * nrg; item += NT) {
+        const int rg = item / nof;
+        const int cf = item - rg * nof;  // flat output column inside the strip
+        const int oxl = cf / Ci;
+        const int c = cf - oxl * Ci;
+        const int xs = sxsize[oxl];
+        const float* wr = Ws + oxl * P.Kw;
+        const float* vs = Vs + (size_t)(rg * RPT) * vw + (sxmin[oxl] * Ci + c - fl0);
+        float h[RPT];
+#pragma unroll
+        for (int r = 0; r < RPT; r++) h[r] = 0.f;
+        for (int j = 0; j < xs; j++) {
+          const float wj = wr[j];
+#pragma unroll
+          for (int r = 0; r < RPT; r++) h[r] = fmaf(wj, vs[(size_t)r * vw + j * Ci], h[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < RPT; r++) {
+          const int rowi = rg * RPT + r;
+          if (rowi < cnt) op[(int64_t)(gbase + rowi) * P.lout.stride_h + cf] = h[r];
+        }
+      }
+      __syncthreads();
+      gbase += cnt;
+      cnt = 0;
+    };
+
+    int64_t y = yA;
+    for (; y + U <= yB; y += U) {
       float v[U][VEC];
-      Rec<A> rec[U];
+      float4 rq[U][RS4];
 #pragma unroll
-      for (int i = 0; i < U; i++) {
-        if (y + i < yB) {
-          if (valid) VLoad<in_t, VEC>::ld(ip + (y + i) * P.lin.stride_h, v[i]);
-          else {
+      for (int i = 0; i < U; i++) VLoad<in_t, VEC>::ld(ip + i * stride_h, v[i]);
 #pragma unroll
-            for (int e = 0; e < VEC; e++) v[i][e] = 0.f;
-          }
-          rec[i] = load_rec<A>(P.slot_h, P.RS, y + i);
-        }
-      }
+      for (int i = 0; i < U; i++)
 #pragma unroll
-      for (int i = 0; i < U; i++) {
-        if (y + i < yB) {
-          // ---- vertical filter: A FMAs per element, weights warp-uniform
+        for (int q = 0; q < RS4; q++) rq[i][q] = __ldg(rp + i * RS4 + q);
+      ip += U * stride_h;
+      rp += U * RS4;
 #pragma unroll
-          for (int a = 0; a < A; a++)
-#pragma unroll
-            for (int e = 0; e < VEC; e++) acc[a][e] = fmaf(rec[i].w[a], v[i][e], acc[a][e]);
-          const int nfl = rec[i].packed >> 24;
-          if (nfl) {
-            const int fo = rec[i].packed & 0xffffff;
-#pragma unroll
-            for (int k = 0; k < A; k++) {
-              if (k < nfl) {
-                const int o = fo + k;
-                const int slot = o % A;
-                const bool inr = (o >= oyA) && (o < oyB);
-                float* dst = Vs + (size_t)cnt * P.vw + VEC * t;
-#pragma unroll
-                for (int a = 0; a < A; a++) {
-                  if (a == slot) {
-                    if (inr && valid) store_vec<VEC>(dst, acc[a]);
-#pragma unroll
-                    for (int e = 0; e < VEC; e++) acc[a][e] = 0.f;
-                  }
-                }
-                if (inr) cnt++;
-              }
-            }
-          }
-        }
-      }
-      if (cnt >= P.tg || (y + U >= yB && cnt > 0)) {
-        // ---- horizontal filter over the buffered rows [gbase, gbase+cnt)
-        __syncthreads();
-        const int nrg = (cnt + RPT - 1) / RPT;
-        for (int item = t; item < nof * nrg; item += NT) {
-          const int rg = item / nof;
-          const int cf = item - rg * nof;  // flat output column inside the strip
-          const int oxl = cf / Ci;
-          const int c = cf - oxl * Ci;
-          const int xs = sxsize[oxl];
-          const float* wr = Ws + oxl * P.Kw;
-          const float* vs = Vs + (size_t)(rg * RPT) * P.vw + (sxmin[oxl] * Ci + c - fl0);
-          float h[RPT];
-#pragma unroll
-          for (int r = 0; r < RPT; r++) h[r] = 0.f;
-          for (int j = 0; j < xs; j++) {
-            const float wj = wr[j];
-#pragma unroll
-            for (int r = 0; r < RPT; r++) h[r] = fmaf(wj, vs[(size_t)r * P.vw + j * Ci], h[r]);
-          }
-#pragma unroll
-          for (int r = 0; r < RPT; r++) {
-            const int row = rg * RPT + r;
-            if (row < cnt) op[(int64_t)(gbase + row) * P.lout.stride_h + cf] = h[r];
-          }
-        }
-        __syncthreads();
-        gbase += cnt;
-        cnt = 0;
-      }
+      for (int i = 0; i < U; i++) row(v[i], rq[i]);
+      if (cnt >= P.tg) hphase();
     }
+    for (; y < yB; y++) {
+      float v[VEC];
+      float4 rq[RS4];
+      VLoad<in_t, VEC>::ld(ip, v);
+#pragma unroll
+      for (int q = 0; q < RS4; q++) rq[q] = __ldg(rp + q);
+      ip += stride_h;
+      rp += RS4;
+      row(v, rq);
+    }
+    if (cnt > 0) hphase();
     u = seg_end;
   }
 }
@@ -273,13 +271,15 @@ template <int A, int VEC, typename in_t>
 struct Cfg {
   static constexpr int NT = 256;
   static constexpr int U = 4;
-  static constexpr int TG = 8;  // buffered rows that trigger a horizontal phase
+  static constexpr int TG = 4;  // buffered rows that trigger a horizontal phase
+  // register budget: 64/thread (4 CTAs/SM) when the accumulators are few, else 2-3 CTAs/SM
+  static constexpr int MINB = (A * VEC <= 12) ? 4 : ((A * VEC <= 24) ? 3 : 2);
 };
 
 template <int A, int VEC, typename in_t>
 int launch_cfg(SParams& P, const AxisTables* th, const AxisTables* tw, int device, cudaStream_t stream) {
   using C = Cfg<A, VEC, in_t>;
-  auto kern = aa_stream_kernel<A, VEC, in_t, C::NT, C::U>;
+  auto kern = aa_stream_kernel<A, VEC, in_t, C::NT, C::U, C::MINB>;
   const int cap = C::NT * VEC;  // flat elements one strip may span
   // ---- strip plan: as few, equal strips as fit `cap` flat elements (exact, from host tables)
   const int64_t oW = P.oW;

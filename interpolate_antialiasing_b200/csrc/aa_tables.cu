@@ -218,9 +218,11 @@ __global__ void aa_tables_adj(int64_t in, int64_t out, int K, int KT, const int3
   }
 }
 
-// One thread per input row y: the rotating-slot records used by the streaming kernel's vertical
-// pass.  Record = A weights indexed by (o % A) followed by (first_flush_o | nflush << 24):
-// `nflush` outputs, starting at first_flush_o = omin[y], have y as the LAST row of their window.
+// One thread per input row y: the records used by the streaming kernel's vertical pass.
+// Record = A weights wT[y][0..A) (k-th weight belongs to output omin[y]+k, the k-th OLDEST output row
+// still open at y), followed by (first_flush_o | nflush << 24): the `nflush` oldest open outputs,
+// starting at first_flush_o = omin[y], have y as the LAST row of their window.  Because the outputs
+// that end at y are exactly the ones missing from row y+1's range, omin[y+1] = omin[y] + nflush.
 __global__ void aa_tables_slots(int64_t in, int A, int RS, int KT, const int32_t* __restrict__ xmin,
                                 const int32_t* __restrict__ xsize, const int32_t* __restrict__ omin,
                                 const int32_t* __restrict__ osize, const float* __restrict__ wT,
@@ -233,7 +235,7 @@ __global__ void aa_tables_slots(int64_t in, int A, int RS, int KT, const int32_t
   int nflush = 0;
   for (int k = 0; k < n && k < A; k++) {
     const int o = o0 + k;
-    rec[o % A] = wT[y * KT + k];
+    rec[k] = wT[y * KT + k];
     if ((int64_t)xmin[o] + xsize[o] - 1 == y) nflush++;
   }
   rec[A] = __int_as_float(o0 | (nflush << 24));
