@@ -74,8 +74,8 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-BandedAxis fwd_axis(const AxisTables* t) { return BandedAxis{t->xmin, t->xsize, t->w, t->K, t->in, t->out}; }
-BandedAxis adj_axis(const AxisTables* t) { return BandedAxis{t->omin, t->osize, t->wT, t->KT, t->out, t->in}; }
+BandedAxis fwd_axis(const AxisTables* t) { return BandedAxis{t->xmin, t->xsize, t->w, t->K, t->in, t->out, t->h_xmin.data(), t->h_xsize.data()}; }
+BandedAxis adj_axis(const AxisTables* t) { return BandedAxis{t->omin, t->osize, t->wT, t->KT, t->out, t->in, t->h_omin.data(), t->h_osize.data()}; }
 
 __global__ void widen_i32_i64(const int32_t* __restrict__ a, int64_t* __restrict__ b, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,6 +108,14 @@ int forward_impl(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter
   if ((rc = get_axis_tables(in->device, in->h, out->h, filter, align, tdtype, stream, &th)) != AA_OK) return rc;
   if ((rc = get_axis_tables(in->device, in->w, out->w, filter, align, tdtype, stream, &tw)) != AA_OK) return rc;
   if (!(flags & AA_FLAG_FORCE_GENERAL) && tdtype == AA_F32) {
+    // few taps on both axes (near scale 1 / upsampling): output-bound -> tile kernel;
+    // otherwise (downsampling): input-bound -> streaming kernel.
+    const bool few_taps = th->xsize_max <= 7 && tw->xsize_max <= 7;
+    if (few_taps && !(flags & AA_FLAG_FORCE_STREAM)) {
+      rc = launch_tile(in->data, in->dtype, lin, out->data, lout, fwd_axis(th.get()), fwd_axis(tw.get()), th->xsize_max,
+                       tw->xsize_max, stream);
+      if (rc != AA_ERR_UNSUPPORTED) return rc;
+    }
     rc = launch_stream(in->data, in->dtype, lin, out->data, lout, th.get(), tw.get(), in->h, in->w, out->h, out->w,
                        flags, stream);
     if (rc == AA_OK) return rc;
@@ -207,7 +215,6 @@ int aa_resize_forward(const aa_tensor_desc* in, const aa_tensor_desc* out, int f
 
 int aa_resize_backward(const aa_tensor_desc* gout, const aa_tensor_desc* gin, int filter, int align_corners, uint32_t flags,
                        void* cuda_stream) {
-  (void)flags;
   int rc;
   Layout lo, li;
   if ((rc = check_filter(filter)) != AA_OK) return rc;
@@ -219,6 +226,11 @@ int aa_resize_backward(const aa_tensor_desc* gout, const aa_tensor_desc* gin, in
   std::shared_ptr<AxisTables> th, tw;
   if ((rc = get_axis_tables(gout->device, gin->h, gout->h, filter, align_corners, gout->dtype, stream, &th)) != AA_OK) return rc;
   if ((rc = get_axis_tables(gout->device, gin->w, gout->w, filter, align_corners, gout->dtype, stream, &tw)) != AA_OK) return rc;
+  if (gout->dtype == AA_F32 && !(flags & AA_FLAG_FORCE_GENERAL)) {
+    rc = launch_tile(gout->data, gout->dtype, lo, gin->data, li, adj_axis(th.get()), adj_axis(tw.get()), th->kt_max,
+                     tw->kt_max, stream);
+    if (rc != AA_ERR_UNSUPPORTED) return rc;
+  }
   return launch_general(gout->data, gout->dtype, lo, gin->data, gin->dtype, li, adj_axis(th.get()), adj_axis(tw.get()),
                         /*exact=*/false, stream);
 }

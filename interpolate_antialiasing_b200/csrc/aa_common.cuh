@@ -66,7 +66,7 @@ struct AxisTables {
   int slot_RS = 0;           // record stride in 32-bit words = roundup4(A+1)
   float* slot = nullptr;     // [in][RS]: A weights by slot (o % A), then (first_flush_o | nflush<<24)
   // host mirrors of the integer tables (for launch planning)
-  std::vector<int32_t> h_xmin, h_xsize;
+  std::vector<int32_t> h_xmin, h_xsize, h_omin, h_osize;
   cudaEvent_t ready = nullptr;  // recorded on the building stream
   ~AxisTables();
 };
@@ -101,6 +101,8 @@ struct BandedAxis {  // one axis of a banded separable apply: out index i reads 
   const void* w;  // [n_out * pitch]
   int pitch;
   int64_t n_in, n_out;
+  const int32_t* h_start;  // host mirrors of start/size (launch planning)
+  const int32_t* h_size;
 };
 
 // General gather-form tile kernel: out = Ah * in * Aw^T per plane, horizontal pass first.
@@ -108,6 +110,12 @@ struct BandedAxis {  // one axis of a banded separable apply: out index i reads 
 int launch_general(const void* in, int in_dtype, const Layout& lin, void* out, int out_dtype,
                    const Layout& lout, const BandedAxis& ah, const BandedAxis& aw, bool exact,
                    cudaStream_t stream);
+
+// Tile kernel for gathers with few taps (backward of downsampling, forward upsampling): input patch
+// in shared memory -> horizontal pass -> shared memory -> vertical pass -> 128-bit stores.  f32 out,
+// f32/u8 in.  Returns AA_ERR_UNSUPPORTED when the patch would not fit so the caller can fall back.
+int launch_tile(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout,
+                const BandedAxis& ah, const BandedAxis& aw, int kh_max, int kw_max, cudaStream_t stream);
 
 // Streaming fused kernel (downsampling in both axes, f32/u8 in, f32 out).  Returns
 // AA_ERR_UNSUPPORTED when not eligible so the caller can fall back to launch_general.

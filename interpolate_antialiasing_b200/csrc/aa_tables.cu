@@ -322,9 +322,13 @@ int build_tables(AxisTables* t, cudaStream_t stream) {
   TableMeta h = {};
   t->h_xmin.resize(out);
   t->h_xsize.resize(out);
+  t->h_omin.resize(in);
+  t->h_osize.resize(in);
   AA_CUDA_TRY(cudaMemcpyAsync(&h, meta, sizeof(h), cudaMemcpyDeviceToHost, stream));
   AA_CUDA_TRY(cudaMemcpyAsync(t->h_xmin.data(), t->xmin, sizeof(int32_t) * out, cudaMemcpyDeviceToHost, stream));
   AA_CUDA_TRY(cudaMemcpyAsync(t->h_xsize.data(), t->xsize, sizeof(int32_t) * out, cudaMemcpyDeviceToHost, stream));
+  AA_CUDA_TRY(cudaMemcpyAsync(t->h_omin.data(), t->omin, sizeof(int32_t) * in, cudaMemcpyDeviceToHost, stream));
+  AA_CUDA_TRY(cudaMemcpyAsync(t->h_osize.data(), t->osize, sizeof(int32_t) * in, cudaMemcpyDeviceToHost, stream));
   AA_CUDA_TRY(cudaStreamSynchronize(stream));  // cache miss only
   t->xsize_max = h.xsize_max;
   t->kt_max = h.kt_max;

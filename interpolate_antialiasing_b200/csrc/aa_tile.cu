@@ -1,0 +1,268 @@
+// aa_tile.cu -- K3: gather-form tile kernel for banded separable applies with FEW taps per output
+// (sm_100a).  This is the shape of
+//   * the backward (adjoint) pass of a downsampling forward: grad_in = Wh^T * grad_out * Ww, every
+//     grad_input element gathers <= KT (3 bilinear, 5 bicubic) grad_output rows/columns -- no atomics, no
+//     zero-fill pass (replaces /root/reference/step_two_dot_two/aa_interpolation_backward_impl.h:185-219,
+//     whose scatter loop2d :80-108 + zero_() :215 it supersedes);
+//   * the forward pass near scale 1 and when upsampling (K = 3..7 taps, aa_interpolation_impl.h:60-87).
+// Such passes are output-(write-)bound, so the kernel is organised around the OUTPUT tile: one CTA
+// produces TY x TXF flat outputs of one plane.
+//   stage 0  the input patch the tile depends on -> shared memory (coalesced, zero padded so the tap
+//            loops below need no bounds checks);
+//   stage 1  horizontal pass: one thread per flat output column, its <= KW weights live in registers,
+//            walks the patch rows -> T[rows][TXF] in shared memory;
+//   stage 2  vertical pass: one thread per 4 consecutive flat columns, per output row one broadcast
+//            LDS.128 fetches {weights, first row}, then KH x (LDS.128 + 4 FMA) and one 128-bit store.
+// Tap counts KH/KW are template parameters (loops fully unrolled); weights beyond a window's true
+// size are zeroed in-kernel.  Summation: horizontal then vertical, FMA, ascending taps (the
+// bit-exact non-FMA order is aa_general.cu's job).
+#include <algorithm>
+
+#include "aa_common.cuh"
+
+namespace aa {
+namespace {
+
+constexpr int TXV = 64;         // float4 columns per tile
+constexpr int TXF = TXV * 4;    // flat output columns per tile (= threads: one column each in stage 1)
+constexpr int NTY = 4;          // thread rows in stages 0 and 2
+constexpr int NT = TXV * NTY;   // 256 threads
+constexpr int TY = 32;          // output rows per tile
+
+struct TParams {
+  const void* in;
+  float* out;
+  Layout lin, lout;
+  int Ci;
+  const int32_t *h_start, *h_size, *w_start, *w_size;
+  const float *h_w, *w_w;
+  int h_pitch, w_pitch;
+  int in_h, in_wf, out_h, out_wf;  // flat widths (pixels * Ci)
+  int tiles_x, tiles_y;
+  int pr;    // rows of patch / T buffers (max input rows per tile + KH - 1)
+  int pcp;   // patch pitch in floats (max input flat cols per tile + (KW-1)*Ci, padded)
+  int vec_store;  // rows of out are 16-byte aligned -> float4 stores
+};
+
+template <typename in_t> __device__ __forceinline__ float ldf(const in_t* p) { return (float)__ldg(p); }
+
+template <int KH, int KW, typename in_t>
+__global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
+  constexpr int HR = (KH + 1 + 3) / 4;  // float4 per row record {w[KH], first T row}
+  extern __shared__ __align__(16) float smem[];
+  float* Ts = smem;                                   // [pr][TXF]
+  float4* hrec = reinterpret_cast<float4*>(Ts + (size_t)P.pr * TXF);  // [TY][HR]
+  float* patch = reinterpret_cast<float*>(hrec + TY * HR);             // [pr][pcp]
+  const int tid = threadIdx.x;
+  const int tx = tid % TXV, ty = tid / TXV;
+  int b = blockIdx.x;
+  const int tile_x = b % P.tiles_x; b /= P.tiles_x;
+  const int tile_y = b % P.tiles_y; b /= P.tiles_y;
+  const int64_t plane = b;
+  const int Ci = P.Ci;
+  const in_t* ip = (const in_t*)P.in + (plane / P.lin.Cp) * P.lin.stride_n + (plane % P.lin.Cp) * P.lin.stride_p;
+  float* op = P.out + (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p;
+
+  // tile extents (starts and ends are non-decreasing in the output index)
+  const int oy0 = tile_y * TY, oy1 = min(P.out_h, oy0 + TY);
+  const int of0 = tile_x * TXF, of1 = min(P.out_wf, of0 + TXF);
+  const int r0 = __ldg(P.h_start + oy0), r1 = __ldg(P.h_start + oy1 - 1) + __ldg(P.h_size + oy1 - 1);
+  const int oxa = of0 / Ci, oxb = (of1 - 1) / Ci;
+  const int c0 = __ldg(P.w_start + oxa) * Ci, c1 = (__ldg(P.w_start + oxb) + __ldg(P.w_size + oxb)) * Ci;
+  const int nr = r1 - r0, nc = c1 - c0;
+  const int prt = nr + KH - 1;             // T / patch rows touched by the unrolled tap loops
+  const int pct = nc + (KW - 1) * Ci;      // patch columns touched
+
+  // ---- per-row records for stage 2
+  if (tid < TY) {
+    const int oy = oy0 + tid;
+    float rec[HR * 4];
+#pragma unroll
+    for (int k = 0; k < HR * 4; k++) rec[k] = 0.f;
+    if (oy < oy1) {
+      const int st = __ldg(P.h_start + oy), sz = __ldg(P.h_size + oy);
+      const float* hr = P.h_w + (int64_t)oy * P.h_pitch;
+#pragma unroll
+      for (int k = 0; k < KH; k++) rec[k] = k < sz ? __ldg(hr + k) : 0.f;
+      rec[KH] = __int_as_float((st - r0) * TXF);
+    }
+#pragma unroll
+    for (int q = 0; q < HR; q++) hrec[tid * HR + q] = make_float4(rec[4 * q], rec[4 * q + 1], rec[4 * q + 2], rec[4 * q + 3]);
+  }
+  // ---- stage 0: input patch -> shared (zero padded).  All copies of a thread are in flight at once:
+  // f32 goes global->shared with cp.async (LDGSTS, zero-fill via src-size 0), u8 through registers in
+  // batches of 8 loads.
+  {
+    const in_t* src = ip + (int64_t)r0 * P.lin.stride_h + c0;
+    if constexpr (sizeof(in_t) == 4) {
+      for (int r = ty; r < prt; r += NTY) {
+        const in_t* srow = src + (int64_t)r * P.lin.stride_h;
+        const uint32_t drow = (uint32_t)__cvta_generic_to_shared(patch + r * P.pcp);
+        const bool rok = r < nr;
+        for (int c = tx; c < pct; c += TXV) {
+          const bool ok = rok && c < nc;
+          const in_t* g = ok ? srow + c : src;  // any valid address when zero-filling
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(drow + 4u * c), "l"(g), "r"(ok ? 4 : 0) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    } else {
+      constexpr int B = 8;
+      const int ncol_it = (pct + TXV - 1) / TXV;       // column iterations per row
+      const int nrow_it = (prt - ty + NTY - 1) / NTY;  // row iterations of this thread
+      const int total = nrow_it > 0 ? nrow_it * ncol_it : 0;
+      for (int i0 = 0; i0 < total; i0 += B) {
+        float v[B];
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+          const int i = i0 + j;
+          const int r = ty + (i / ncol_it) * NTY, c = tx + (i % ncol_it) * TXV;
+          v[j] = (i < total && r < nr && c < nc) ? ldf(src + (int64_t)r * P.lin.stride_h + c) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+          const int i = i0 + j;
+          const int r = ty + (i / ncol_it) * NTY, c = tx + (i % ncol_it) * TXV;
+          if (i < total && c < pct) patch[r * P.pcp + c] = v[j];
+        }
+      }
+    }
+  }
+  // ---- stage 1 setup: this thread's flat output column
+  float w[KW];
+  int soff = 0;
+  {
+    const int of = of0 + tid;
+    if (of < of1) {
+      const int ox = of / Ci;
+      const int c = of - ox * Ci;
+      const int st = __ldg(P.w_start + ox), sz = __ldg(P.w_size + ox);
+      const float* wr = P.w_w + (int64_t)ox * P.w_pitch;
+#pragma unroll
+      for (int k = 0; k < KW; k++) w[k] = k < sz ? __ldg(wr + k) : 0.f;
+      soff = st * Ci + c - c0;
+    } else {
+#pragma unroll
+      for (int k = 0; k < KW; k++) w[k] = 0.f;
+    }
+  }
+  if constexpr (sizeof(in_t) == 4) asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // ---- stage 1: horizontal pass -> Ts
+  {
+    const float* src = patch + soff;
+    float* dst = Ts + tid;
+#pragma unroll 4
+    for (int r = 0; r < prt; r++) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < KW; k++) a = fmaf(src[k * Ci], w[k], a);
+      *dst = a;
+      src += P.pcp;
+      dst += TXF;
+    }
+  }
+  __syncthreads();
+  // ---- stage 2: vertical pass + store
+  const int ofv = of0 + 4 * tx;
+  if (ofv < of1) {
+    float* dst = op + (int64_t)(oy0 + ty) * P.lout.stride_h + ofv;
+    const int64_t dstep = (int64_t)NTY * P.lout.stride_h;
+    const bool full = P.vec_store && (ofv + 4 <= of1);
+    for (int oyl = ty; oyl < oy1 - oy0; oyl += NTY, dst += dstep) {
+      float rec[HR * 4];
+#pragma unroll
+      for (int q = 0; q < HR; q++) {
+        const float4 t4 = hrec[oyl * HR + q];
+        rec[4 * q] = t4.x; rec[4 * q + 1] = t4.y; rec[4 * q + 2] = t4.z; rec[4 * q + 3] = t4.w;
+      }
+      const float4* src = reinterpret_cast<const float4*>(Ts + __float_as_int(rec[KH]) + 4 * tx);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < KH; k++) {
+        const float4 v = src[k * TXV];
+        a.x = fmaf(v.x, rec[k], a.x); a.y = fmaf(v.y, rec[k], a.y); a.z = fmaf(v.z, rec[k], a.z); a.w = fmaf(v.w, rec[k], a.w);
+      }
+      if (full) {
+        *reinterpret_cast<float4*>(dst) = a;
+      } else {
+        dst[0] = a.x;
+        if (ofv + 1 < of1) dst[1] = a.y;
+        if (ofv + 2 < of1) dst[2] = a.z;
+        if (ofv + 3 < of1) dst[3] = a.w;
+      }
+    }
+  }
+}
+
+template <int KH, int KW, typename in_t>
+int launch_k(TParams& P, int64_t nblocks, int nr_max, int nc_max, cudaStream_t stream) {
+  constexpr int HR = (KH + 1 + 3) / 4;
+  P.pr = nr_max + KH - 1;
+  int pcp = nc_max + (KW - 1) * P.Ci;
+  pcp |= 1;  // odd pitch
+  P.pcp = pcp;
+  const size_t smem = sizeof(float) * ((size_t)P.pr * TXF + (size_t)TY * HR * 4 + (size_t)P.pr * P.pcp);
+  if (smem > 100 * 1024) return fail(AA_ERR_UNSUPPORTED, "tile: input patch too large; use the streaming/general path");
+  auto kern = aa_tile_kernel<KH, KW, in_t>;
+  if (smem > 48 * 1024) AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)nblocks, NT, smem, stream>>>(P);
+  AA_LAUNCH_CHECK("aa_tile_kernel");
+  return AA_OK;
+}
+
+template <int KH, typename in_t>
+int launch_kh(TParams& P, int kw, int64_t nb, int nr, int nc, cudaStream_t s) {
+  if (kw <= 2) return launch_k<KH, 2, in_t>(P, nb, nr, nc, s);
+  if (kw <= 3) return launch_k<KH, 3, in_t>(P, nb, nr, nc, s);
+  if (kw <= 5) return launch_k<KH, 5, in_t>(P, nb, nr, nc, s);
+  if (kw <= 7) return launch_k<KH, 7, in_t>(P, nb, nr, nc, s);
+  return fail(AA_ERR_UNSUPPORTED, "tile: more than 7 horizontal taps");
+}
+
+template <typename in_t>
+int launch_in(TParams& P, int kh, int kw, int64_t nb, int nr, int nc, cudaStream_t s) {
+  if (kh <= 2) return launch_kh<2, in_t>(P, kw, nb, nr, nc, s);
+  if (kh <= 3) return launch_kh<3, in_t>(P, kw, nb, nr, nc, s);
+  if (kh <= 5) return launch_kh<5, in_t>(P, kw, nb, nr, nc, s);
+  if (kh <= 7) return launch_kh<7, in_t>(P, kw, nb, nr, nc, s);
+  return fail(AA_ERR_UNSUPPORTED, "tile: more than 7 vertical taps");
+}
+
+}  // namespace
+
+int launch_tile(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout,
+                const BandedAxis& ah, const BandedAxis& aw, int kh_max, int kw_max, cudaStream_t stream) {
+  if (in_dtype != AA_F32 && in_dtype != AA_U8) return fail(AA_ERR_UNSUPPORTED, "tile: f32/u8 input only");
+  if (kh_max > 7 || kw_max > 7) return fail(AA_ERR_UNSUPPORTED, "tile: more than 7 taps; use the streaming/general path");
+  const int Ci = lin.Ci;
+  if (aw.n_out * Ci >= (1ll << 30) || aw.n_in * Ci >= (1ll << 30) || ah.n_out >= (1ll << 30)) return fail(AA_ERR_UNSUPPORTED, "tile: size limits");
+  TParams P;
+  P.in = in; P.out = (float*)out; P.lin = lin; P.lout = lout; P.Ci = Ci;
+  P.h_start = ah.start; P.h_size = ah.size; P.h_w = (const float*)ah.w; P.h_pitch = ah.pitch;
+  P.w_start = aw.start; P.w_size = aw.size; P.w_w = (const float*)aw.w; P.w_pitch = aw.pitch;
+  P.in_h = (int)ah.n_in; P.in_wf = (int)(aw.n_in * Ci); P.out_h = (int)ah.n_out; P.out_wf = (int)(aw.n_out * Ci);
+  P.tiles_x = (P.out_wf + TXF - 1) / TXF;
+  P.tiles_y = (P.out_h + TY - 1) / TY;
+  // exact patch plan from the host mirrors of the tables
+  int64_t nr = 1, nc = 1;
+  for (int64_t y0 = 0; y0 < P.out_h; y0 += TY) {
+    const int64_t y1 = std::min<int64_t>(P.out_h, y0 + TY) - 1;
+    nr = std::max<int64_t>(nr, (int64_t)ah.h_start[y1] + ah.h_size[y1] - ah.h_start[y0]);
+  }
+  for (int64_t f0 = 0; f0 < P.out_wf; f0 += TXF) {
+    const int64_t f1 = std::min<int64_t>(P.out_wf, f0 + TXF) - 1;
+    const int64_t x0 = f0 / Ci, x1 = f1 / Ci;
+    nc = std::max<int64_t>(nc, ((int64_t)aw.h_start[x1] + aw.h_size[x1] - aw.h_start[x0]) * Ci);
+  }
+  if (nr > 512 || nc > 4096) return fail(AA_ERR_UNSUPPORTED, "tile: input patch too large; use the streaming/general path");
+  P.vec_store = (((uintptr_t)out) % 16 == 0) && (lout.stride_h % 4 == 0) && (lout.stride_n % 4 == 0) &&
+                (lout.Cp == 1 || lout.stride_p % 4 == 0);
+  const int64_t nblocks = (int64_t)P.tiles_x * P.tiles_y * lin.planes;
+  if (nblocks <= 0) return AA_OK;
+  if (nblocks >= (1ll << 31)) return fail(AA_ERR_UNSUPPORTED, "tile: too many tiles");
+  if (in_dtype == AA_F32) return launch_in<float>(P, kh_max, kw_max, nblocks, (int)nr, (int)nc, stream);
+  return launch_in<uint8_t>(P, kh_max, kw_max, nblocks, (int)nr, (int)nc, stream);
+}
+
+}  // namespace aa

@@ -67,3 +67,26 @@ if "cfg4" in which:
     print(f"{'cfg4 backward bilinear 64x3x128^2 -> 512^2':58s} med {med*1e3:9.1f} us  best {best*1e3:9.1f} us  {b/med/1e6:8.1f} GB/s  {b/med/1e6/PEAK*100:5.1f}% of peak")
     x = torch.rand((64, 3, 512, 512), generator=g, device=dev)
     run("cfg4 forward 64x3x512^2->128^2 bilinear AUTO", x, (128, 128), "linear", capi.FLAG_AUTO, b)
+
+if "sweep" in which:
+    # cfg5: scale sweep 0.125x-2x, C in {1,3,4}, channels_first vs channels_last, both filters; >= 1 GB per point
+    Hin = Win = 1024
+    rows = []
+    for mode in ("linear", "cubic"):
+        for C in (1, 3, 4):
+            for cl in (False, True):
+                for s in (0.125, 0.25, 0.333, 0.5, 0.75, 1.0, 1.5, 2.0):
+                    oh = ow = max(1, round(Hin * s))
+                    per_img = C * (Hin * Win + oh * ow) * 4
+                    N = max(1, int(1.0e9 // per_img) + 1)
+                    x = torch.rand((N, C, Hin, Win), generator=g, device=dev) * 255
+                    if cl:
+                        x = x.contiguous(memory_format=torch.channels_last)
+                    try:
+                        out = capi.resize_forward(x, (oh, ow), mode, False, capi.FLAG_AUTO)
+                        med, best = timeit(lambda: capi.resize_forward(x, (oh, ow), mode, False, capi.FLAG_AUTO, out=out), iters=5, warm=2)
+                        gbs = N * per_img / med / 1e6
+                        print(f"sweep {mode:6s} C={C} {'CL' if cl else 'CF'} s={s:5.3f} N={N:3d} {med*1e3:9.1f} us {gbs:8.1f} GB/s {gbs/PEAK*100:5.1f}%", flush=True)
+                    except capi.AAError as e:
+                        print(f"sweep {mode} C={C} cl={cl} s={s} ERROR {e}", flush=True)
+                    del x
