@@ -25,92 +25,11 @@
 // separable sum with fp32 rounding of the intermediate; the difference is pure rounding
 // (measured <= 1.3e-4 abs / 2.3e-6 rel on a 0..255 scale against the reference, tolerance
 // 1e-3 abs / 1e-5 rel -- tests/test_forward_gpu.py).  The bit-exact order lives in aa_general.cu.
-#include <algorithm>
-
-#include "aa_common.cuh"
+#include "aa_stream_common.cuh"
 
 namespace aa {
+using namespace stream_detail;
 namespace {
-
-constexpr int kMaxA = 6;
-
-struct SParams {
-  const void* in;
-  float* out;
-  Layout lin, lout;
-  int Ci;
-  int64_t H, oH, oW;
-  const float* slot_h;  // [H][RS]
-  int RS;
-  const int32_t *xmin_h, *xsize_h;
-  const int32_t *xmin_w, *xsize_w;
-  const float* w_w;  // [oW][Kw]
-  int Kw;
-  int n_strips, strip_ox;
-  int64_t total_units;  // planes * n_strips * oH
-  int vw;               // shared-memory row pitch of Vs in floats
-  int vr;               // rows of Vs
-  int tg;               // buffered rows that trigger a horizontal phase
-};
-
-// ---- vector loads (read-once data: bypass L1 allocation) -------------------------------------
-template <typename in_t, int VEC> struct VLoad;
-template <> struct VLoad<float, 4> {
-  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
-  }
-};
-template <> struct VLoad<float, 2> {
-  static __device__ __forceinline__ void ld(const float* p, float (&v)[2]) {
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "l"(p));
-  }
-};
-template <> struct VLoad<float, 1> {
-  static __device__ __forceinline__ void ld(const float* p, float (&v)[1]) {
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v[0]) : "l"(p));
-  }
-};
-__device__ __forceinline__ void unpack4(uint32_t w, float* v) {
-  v[0] = (float)(w & 0xffu);
-  v[1] = (float)((w >> 8) & 0xffu);
-  v[2] = (float)((w >> 16) & 0xffu);
-  v[3] = (float)(w >> 24);
-}
-template <> struct VLoad<uint8_t, 16> {
-  static __device__ __forceinline__ void ld(const uint8_t* p, float (&v)[16]) {
-    uint32_t a, b, c, d;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
-    unpack4(a, v); unpack4(b, v + 4); unpack4(c, v + 8); unpack4(d, v + 12);
-  }
-};
-template <> struct VLoad<uint8_t, 8> {
-  static __device__ __forceinline__ void ld(const uint8_t* p, float (&v)[8]) {
-    uint32_t a, b;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
-    unpack4(a, v); unpack4(b, v + 4);
-  }
-};
-template <> struct VLoad<uint8_t, 4> {
-  static __device__ __forceinline__ void ld(const uint8_t* p, float (&v)[4]) {
-    uint32_t a;
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(a) : "l"(p));
-    unpack4(a, v);
-  }
-};
-
-template <int VEC> __device__ __forceinline__ void store_vec(float* dst, const float* a) {
-  if constexpr (VEC % 4 == 0) {
-#pragma unroll
-    for (int i = 0; i < VEC / 4; i++)
-      reinterpret_cast<float4*>(dst)[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
-  } else if constexpr (VEC == 2) {
-    *reinterpret_cast<float2*>(dst) = make_float2(a[0], a[1]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < VEC; i++) dst[i] = a[i];
-  }
-}
 
 // A     rotating accumulator slots (>= max outputs covering one input row)
 // VEC   flat elements per thread per row
@@ -156,7 +75,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
       cur_strip = s;
       __syncthreads();
     }
-    const int fl0 = (sxmin[0] * Ci) & ~(VEC - 1);                            // first flat element of the strip
+    const int fl0 = (sxmin[0] * Ci) & ~(P.aln - 1);                          // first flat element of the strip
     const int fl_end = (sxmin[ox1 - ox0 - 1] + sxsize[ox1 - ox0 - 1]) * Ci;  // one past the last
     const bool valid = fl0 + VEC * t < fl_end;
     // threads beyond the strip re-read its first vector (a legal address) and never store
@@ -280,47 +199,9 @@ template <int A, int VEC, typename in_t>
 int launch_cfg(SParams& P, const AxisTables* th, const AxisTables* tw, int device, cudaStream_t stream) {
   using C = Cfg<A, VEC, in_t>;
   auto kern = aa_stream_kernel<A, VEC, in_t, C::NT, C::U, C::MINB>;
-  const int cap = C::NT * VEC;  // flat elements one strip may span
-  // ---- strip plan: as few, equal strips as fit `cap` flat elements (exact, from host tables)
-  const int64_t oW = P.oW;
-  const int Ci = P.Ci;
-  int n_strips = 1, strip_ox = (int)oW;
-  int64_t max_extent = 0;
-  for (;; n_strips++) {
-    if (n_strips > oW) return fail(AA_ERR_UNSUPPORTED, "stream: a single output column spans more than one strip");
-    strip_ox = (int)((oW + n_strips - 1) / n_strips);
-    bool ok = strip_ox <= 512;
-    max_extent = 0;
-    for (int64_t a = 0; ok && a < oW; a += strip_ox) {
-      const int64_t b = std::min<int64_t>(oW, a + strip_ox) - 1;
-      const int64_t f0 = ((int64_t)tw->h_xmin[a] * Ci) & ~(int64_t)(VEC - 1);
-      const int64_t f1 = ((int64_t)tw->h_xmin[b] + tw->h_xsize[b]) * Ci;
-      if (f1 - f0 > cap) ok = false;
-      max_extent = std::max(max_extent, f1 - f0);
-    }
-    if (ok) break;
-  }
-  n_strips = (int)((oW + strip_ox - 1) / strip_ox);
-  P.n_strips = n_strips;
-  P.strip_ox = strip_ox;
-  constexpr int VA = VEC > 4 ? VEC : 4;
-  P.vw = (int)((max_extent + VA - 1) / VA * VA);
-  // ---- row buffer plan: most rows that can finish inside one U-row batch (exact, from host tables)
-  int fmax = 1;
-  {
-    const int64_t oH = P.oH;
-    int64_t lo = 0;
-    for (int64_t o = 0; o < oH; o++) {  // ends are non-decreasing
-      const int64_t e = (int64_t)th->h_xmin[o] + th->h_xsize[o];
-      while ((int64_t)th->h_xmin[lo] + th->h_xsize[lo] <= e - C::U) lo++;
-      fmax = std::max<int>(fmax, (int)(o - lo + 1));
-    }
-  }
-  P.tg = C::TG;
-  P.vr = (P.tg - 1 + fmax + 3) / 4 * 4;
-  if (P.vr > 32) return fail(AA_ERR_UNSUPPORTED, "stream: too many output rows finish per input batch (upsampling in H)");
-  const int64_t planes = P.lin.planes;
-  P.total_units = planes * n_strips * P.oH;
+  int rc = plan_stream(P, th, tw, C::NT * VEC, VEC, VEC, C::U, C::TG);
+  if (rc != AA_OK) return rc;
+  const int strip_ox = P.strip_ox;
   const size_t smem = sizeof(float) * ((size_t)P.vr * P.vw + (size_t)strip_ox * P.Kw) + sizeof(int) * 2 * (size_t)strip_ox;
   if (smem > 200 * 1024) return fail(AA_ERR_UNSUPPORTED, "stream: shared memory plan too large");
   AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -352,7 +233,6 @@ int launch_A(SParams& P, int in_dtype, int vec, const AxisTables* th, const Axis
 int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout,
                   AxisTables* th, AxisTables* tw, int64_t H, int64_t W, int64_t oH, int64_t oW,
                   uint32_t flags, cudaStream_t stream) {
-  (void)flags;
   if (in_dtype != AA_F32 && in_dtype != AA_U8) return fail(AA_ERR_UNSUPPORTED, "stream: input must be f32 or u8");
   if (th->dtype != AA_F32 || tw->dtype != AA_F32) return fail(AA_ERR_UNSUPPORTED, "stream: f32 tables only");
   if (th->kt_max > kMaxA) return fail(AA_ERR_UNSUPPORTED, "stream: too many output rows per input row (upsampling in H)");
@@ -379,6 +259,7 @@ int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, co
   P.slot_h = th->slot; P.RS = th->slot_RS;
   P.xmin_h = th->xmin; P.xsize_h = th->xsize;
   P.xmin_w = tw->xmin; P.xsize_w = tw->xsize; P.w_w = (const float*)tw->w; P.Kw = tw->K;
+  if (flags & AA_FLAG_STREAM_TMA) return launch_stream_tma(P, A, in_dtype, th, tw, th->device, stream);
   switch (A) {
     case 3: return launch_A<3>(P, in_dtype, vec, th, tw, th->device, stream);
     case 4: return launch_A<4>(P, in_dtype, vec, th, tw, th->device, stream);

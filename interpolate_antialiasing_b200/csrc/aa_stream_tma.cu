@@ -1,0 +1,310 @@
+// aa_stream_tma.cu -- K2, TMA variant: the streaming fused forward kernel with the input row band
+// staged in shared memory by bulk asynchronous copies (cp.async.bulk, the 1-D TMA path; SASS UBLKCP)
+// tracked by mbarriers, instead of per-thread global loads.
+//
+// Same algorithm, tables, work split and numerics as aa_stream.cu (read that header first).  What
+// changes is who moves the bytes:
+//   * warp NWC (the producer) walks the CTA's segments; for every chunk of R input rows it waits for a
+//     free stage (empty mbarrier), arms the stage's full mbarrier with the byte count and issues one
+//     cp.async.bulk per row (a contiguous, 16-byte aligned strip of the row) -- one elected lane, no
+//     registers, up to STAGES*R rows in flight per CTA regardless of what the consumer warps are doing
+//     (the horizontal phase no longer drains the memory pipe);
+//   * the NWC consumer warps wait on the full mbarrier, read their VEC elements per row with one
+//     conflict-free 128-/64-bit LDS, run the vertical FMAs exactly as the LDG variant, and release the
+//     stage (one arrive per warp on the empty mbarrier).
+// Consumer-only synchronisation uses named barrier 1 so the producer warp never takes part.
+#include "aa_stream_common.cuh"
+
+namespace aa {
+using namespace stream_detail;
+namespace {
+
+constexpr int NWC = 8;             // consumer warps
+constexpr int NTC = NWC * 32;      // consumer threads
+constexpr int NT = NTC + 32;       // + one producer warp
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory"); }
+
+// staged-row reads
+template <typename in_t, int VEC> struct SLoad;
+template <> struct SLoad<float, 4> {
+  static __device__ __forceinline__ void ld(const unsigned char* p, float (&v)[4]) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
+};
+template <> struct SLoad<uint8_t, 8> {
+  static __device__ __forceinline__ void ld(const unsigned char* p, float (&v)[8]) {
+    const uint2 q = *reinterpret_cast<const uint2*>(p);
+    unpack4(q.x, v); unpack4(q.y, v + 4);
+  }
+};
+
+// A accumulators per element, VEC elements per thread, R rows per stage, STAGES stages.
+template <int A, int VEC, typename in_t, int R, int STAGES, int MINB>
+__global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int RPT = 4;
+  constexpr int RS4 = (A + 1 + 3) / 4;
+  constexpr int ES = (int)sizeof(in_t);
+  // layout: [stages][R][in_pitch] staged input | Vs[vr][vw] | Ws[strip_ox][Kw] | sxmin | sxsize | mbarriers
+  unsigned char* stage_base = smem_raw;
+  float* Vs = reinterpret_cast<float*>(stage_base + (size_t)STAGES * R * P.in_pitch);
+  float* Ws = Vs + (size_t)P.vr * P.vw;
+  int* sxmin = reinterpret_cast<int*>(Ws + (size_t)P.strip_ox * P.Kw);
+  int* sxsize = sxmin + P.strip_ox;
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sxsize + P.strip_ox) + 7) & ~(uintptr_t)7);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+
+  const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
+  if (t == 0) {
+    for (int i = 0; i < STAGES; i++) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, NWC); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int Ci = P.Ci;
+  const int64_t oH = P.oH;
+  const int64_t stride_h = P.lin.stride_h;
+  const int64_t u_begin = P.total_units * (int64_t)blockIdx.x / gridDim.x;
+  const int64_t u_end = P.total_units * (int64_t)(blockIdx.x + 1) / gridDim.x;
+  int stage = 0;
+  uint32_t phase = 0;
+
+  if (warp == NWC) {
+    // =========================== producer: one elected lane issues the bulk copies ===============
+    if (lane == 0) {
+      for (int64_t u = u_begin; u < u_end;) {
+        const int64_t col = u / oH;
+        const int oyA = (int)(u - col * oH);
+        const int64_t seg_end = min(u_end, (col + 1) * oH);
+        const int oyB = oyA + (int)(seg_end - u);
+        const int64_t plane = col / P.n_strips;
+        const int s = (int)(col - plane * P.n_strips);
+        const int ox0 = s * P.strip_ox;
+        const int ox1 = min((int)P.oW, ox0 + P.strip_ox);
+        const int fl0 = (__ldg(P.xmin_w + ox0) * Ci) & ~(P.aln - 1);
+        const int fl_end = (__ldg(P.xmin_w + ox1 - 1) + __ldg(P.xsize_w + ox1 - 1)) * Ci;
+        const uint32_t row_bytes = (uint32_t)(((fl_end - fl0) * ES + 15) & ~15);
+        const int64_t yA = __ldg(P.xmin_h + oyA);
+        const int64_t yB = (int64_t)__ldg(P.xmin_h + oyB - 1) + __ldg(P.xsize_h + oyB - 1);
+        const in_t* src = (const in_t*)P.in + (plane / P.lin.Cp) * P.lin.stride_n + (plane % P.lin.Cp) * P.lin.stride_p + fl0 + yA * stride_h;
+        for (int64_t y = yA; y < yB; y += R) {
+          const int n = (int)min((int64_t)R, yB - y);
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          mbar_expect_tx(full0 + 8 * stage, row_bytes * n);
+          const uint32_t dst = smem_u32(stage_base + (size_t)stage * R * P.in_pitch);
+          for (int i = 0; i < n; i++) bulk_g2s(dst + i * P.in_pitch, src + i * stride_h, row_bytes, full0 + 8 * stage);
+          src += (int64_t)R * stride_h;
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        u = seg_end;
+      }
+    }
+    return;
+  }
+
+  // =============================== consumers ========================================================
+  const int vw = P.vw;
+  int cur_strip = -1;
+  for (int64_t u = u_begin; u < u_end;) {
+    const int64_t col = u / oH;
+    const int oyA = (int)(u - col * oH);
+    const int64_t seg_end = min(u_end, (col + 1) * oH);
+    const int oyB = oyA + (int)(seg_end - u);
+    const int64_t plane = col / P.n_strips;
+    const int s = (int)(col - plane * P.n_strips);
+    const int ox0 = s * P.strip_ox;
+    const int ox1 = min((int)P.oW, ox0 + P.strip_ox);
+    if (s != cur_strip) {
+      consumer_sync();
+      const int nox = ox1 - ox0;
+      for (int i = t; i < nox * P.Kw; i += NTC) Ws[i] = __ldg(P.w_w + (int64_t)ox0 * P.Kw + i);
+      for (int i = t; i < nox; i += NTC) { sxmin[i] = __ldg(P.xmin_w + ox0 + i); sxsize[i] = __ldg(P.xsize_w + ox0 + i); }
+      cur_strip = s;
+      consumer_sync();
+    }
+    const int fl0 = (sxmin[0] * Ci) & ~(P.aln - 1);
+    const int fl_end = (sxmin[ox1 - ox0 - 1] + sxsize[ox1 - ox0 - 1]) * Ci;
+    const bool valid = fl0 + VEC * t < fl_end;
+    const int64_t yA = __ldg(P.xmin_h + oyA);
+    const int64_t yB = (int64_t)__ldg(P.xmin_h + oyB - 1) + __ldg(P.xsize_h + oyB - 1);
+    const float4* rp = reinterpret_cast<const float4*>(P.slot_h) + yA * RS4;
+    float* op = P.out + (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p + (int64_t)ox0 * Ci;
+    const int nof = (ox1 - ox0) * Ci;
+    float* vdst = Vs + VEC * t;
+    const unsigned char* my_in = stage_base + (size_t)VEC * ES * t;  // + stage*R*in_pitch + i*in_pitch
+
+    float acc[A][VEC];
+#pragma unroll
+    for (int a = 0; a < A; a++)
+#pragma unroll
+      for (int i = 0; i < VEC; i++) acc[a][i] = 0.f;
+    int gbase = oyA;
+    int cnt = 0;
+
+    auto row = [&](const float (&v)[VEC], const float4 (&rq)[RS4]) {
+      const float* rw = reinterpret_cast<const float*>(rq);
+#pragma unroll
+      for (int a = 0; a < A; a++)
+#pragma unroll
+        for (int e = 0; e < VEC; e++) acc[a][e] = fmaf(rw[a], v[e], acc[a][e]);
+      const int packed = __float_as_int(rw[A]);
+      if (packed >> 24) {
+        const int nfl = packed >> 24;
+        int o = packed & 0xffffff;
+#pragma unroll 1
+        for (int k = 0; k < nfl; k++, o++) {
+          if (o >= oyA && o < oyB) {
+            if (valid) store_vec<VEC>(vdst + (size_t)cnt * vw, acc[0]);
+            cnt++;
+          }
+#pragma unroll
+          for (int a = 0; a + 1 < A; a++)
+#pragma unroll
+            for (int e = 0; e < VEC; e++) acc[a][e] = acc[a + 1][e];
+#pragma unroll
+          for (int e = 0; e < VEC; e++) acc[A - 1][e] = 0.f;
+        }
+      }
+    };
+    auto hphase = [&]() {
+      consumer_sync();
+      const int nrg = (cnt + RPT - 1) / RPT;
+      for (int item = t; item < nof * nrg; item += NTC) {
+        const int rg = item / nof;
+        const int cf = item - rg * nof;
+        const int oxl = cf / Ci;
+        const int c = cf - oxl * Ci;
+        const int xs = sxsize[oxl];
+        const float* wr = Ws + oxl * P.Kw;
+        const float* vs = Vs + (size_t)(rg * RPT) * vw + (sxmin[oxl] * Ci + c - fl0);
+        float h[RPT];
+#pragma unroll
+        for (int r = 0; r < RPT; r++) h[r] = 0.f;
+        for (int j = 0; j < xs; j++) {
+          const float wj = wr[j];
+#pragma unroll
+          for (int r = 0; r < RPT; r++) h[r] = fmaf(wj, vs[(size_t)r * vw + j * Ci], h[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < RPT; r++) {
+          const int rowi = rg * RPT + r;
+          if (rowi < cnt) op[(int64_t)(gbase + rowi) * P.lout.stride_h + cf] = h[r];
+        }
+      }
+      consumer_sync();
+      gbase += cnt;
+      cnt = 0;
+    };
+
+    for (int64_t y = yA; y < yB; y += R) {
+      const int n = (int)min((int64_t)R, yB - y);
+      const unsigned char* sp = my_in + (size_t)stage * R * P.in_pitch;
+      mbar_wait(full0 + 8 * stage, phase);
+      if (n == R) {
+        float v[R][VEC];
+        float4 rq[R][RS4];
+#pragma unroll
+        for (int i = 0; i < R; i++) SLoad<in_t, VEC>::ld(sp + i * P.in_pitch, v[i]);
+#pragma unroll
+        for (int i = 0; i < R; i++)
+#pragma unroll
+          for (int q = 0; q < RS4; q++) rq[i][q] = __ldg(rp + i * RS4 + q);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * stage);  // staged rows are in registers: release the stage
+#pragma unroll
+        for (int i = 0; i < R; i++) row(v[i], rq[i]);
+      } else {
+        for (int i = 0; i < n; i++) {
+          float v[VEC];
+          float4 rq[RS4];
+          SLoad<in_t, VEC>::ld(sp + i * P.in_pitch, v);
+#pragma unroll
+          for (int q = 0; q < RS4; q++) rq[q] = __ldg(rp + i * RS4 + q);
+          row(v, rq);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+      }
+      rp += R * RS4;
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      if (cnt >= P.tg || (y + R >= yB && cnt > 0)) hphase();
+    }
+    u = seg_end;
+  }
+}
+
+template <int A, int VEC, typename in_t>
+int launch_tma_cfg(SParams& P, const AxisTables* th, const AxisTables* tw, int device, cudaStream_t stream) {
+  constexpr int R = 4, STAGES = 4;
+  constexpr int MINB = 2;
+  constexpr int ES = (int)sizeof(in_t);
+  auto kern = aa_stream_tma_kernel<A, VEC, in_t, R, STAGES, MINB>;
+  int rc = plan_stream(P, th, tw, NTC * VEC, 16 / ES, VEC, R, 4);
+  if (rc != AA_OK) return rc;
+  P.in_pitch = (P.vw * ES + 15) & ~15;
+  const size_t smem = (size_t)STAGES * R * P.in_pitch + sizeof(float) * ((size_t)P.vr * P.vw + (size_t)P.strip_ox * P.Kw) +
+                      sizeof(int) * 2 * (size_t)P.strip_ox + 8 + 16 * STAGES;
+  if (smem > 200 * 1024) return fail(AA_ERR_UNSUPPORTED, "stream/tma: shared memory plan too large");
+  AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0, sms = 0;
+  AA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+  AA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  if (occ < 1) return fail(AA_ERR_UNSUPPORTED, "stream/tma: kernel does not fit on an SM");
+  int64_t grid = (int64_t)occ * sms;
+  grid = std::max<int64_t>(1, std::min<int64_t>(grid, P.total_units / 4));
+  kern<<<(unsigned)grid, NT, smem, stream>>>(P);
+  AA_LAUNCH_CHECK("aa_stream_tma_kernel");
+  return AA_OK;
+}
+
+template <int A>
+int launch_tma_A(SParams& P, int in_dtype, const AxisTables* th, const AxisTables* tw, int device, cudaStream_t stream) {
+  if (in_dtype == AA_F32) return launch_tma_cfg<A, 4, float>(P, th, tw, device, stream);
+  return launch_tma_cfg<A, 8, uint8_t>(P, th, tw, device, stream);
+}
+
+}  // namespace
+
+int launch_stream_tma(SParams& P, int A, int in_dtype, const AxisTables* th, const AxisTables* tw, int device, cudaStream_t stream) {
+  // cp.async.bulk needs 16-byte aligned global addresses and sizes: base, plane and row strides
+  const int es = in_dtype == AA_F32 ? 4 : 1;
+  const int64_t al = 16 / es;
+  if (((uintptr_t)P.in) % 16 || (P.lin.stride_h % al) || (P.lin.stride_n % al) || (P.lin.Cp > 1 && P.lin.stride_p % al))
+    return fail(AA_ERR_UNSUPPORTED, "stream/tma: input rows are not 16-byte aligned");
+  switch (A) {
+    case 3: return launch_tma_A<3>(P, in_dtype, th, tw, device, stream);
+    case 4: return launch_tma_A<4>(P, in_dtype, th, tw, device, stream);
+    case 5: return launch_tma_A<5>(P, in_dtype, th, tw, device, stream);
+    case 6: return launch_tma_A<6>(P, in_dtype, th, tw, device, stream);
+  }
+  return fail(AA_ERR_UNSUPPORTED, "stream/tma: unsupported accumulator count");
+}
+
+}  // namespace aa

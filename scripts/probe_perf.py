@@ -90,3 +90,27 @@ if "sweep" in which:
                     except capi.AAError as e:
                         print(f"sweep {mode} C={C} cl={cl} s={s} ERROR {e}", flush=True)
                     del x
+
+if "tma" in which:
+    N = 64
+    x = (torch.rand((N, 3, 1080, 1920), generator=g, device=dev) * 255).contiguous(memory_format=torch.channels_last)
+    b = N * 3 * (1080 * 1920 + 224 * 224) * 4
+    ref = capi.resize_forward(x, (224, 224), "linear", False, capi.FLAG_FORCE_STREAM)
+    run("cfg2/4 fp32 CL STREAM (LDG)", x, (224, 224), "linear", capi.FLAG_FORCE_STREAM, b)
+    run("cfg2/4 fp32 CL STREAM (TMA)", x, (224, 224), "linear", capi.FLAG_FORCE_STREAM | capi.FLAG_STREAM_TMA, b)
+    y = capi.resize_forward(x, (224, 224), "linear", False, capi.FLAG_FORCE_STREAM | capi.FLAG_STREAM_TMA)
+    torch.cuda.synchronize()
+    print("TMA vs LDG max abs diff", (y - ref).abs().max().item(), "equal", torch.equal(y, ref))
+    xcf = x.contiguous()
+    run("cfg2/4 fp32 CF STREAM (TMA)", xcf, (224, 224), "linear", capi.FLAG_FORCE_STREAM | capi.FLAG_STREAM_TMA, b)
+    del x, xcf
+    N = 32
+    x = torch.randint(0, 256, (N, 3, 2160, 3840), generator=g, device=dev, dtype=torch.uint8)
+    b = N * 3 * (2160 * 3840 * 1 + 512 * 512 * 4)
+    ref = capi.resize_forward(x, (512, 512), "cubic", False, capi.FLAG_FORCE_STREAM)
+    run("cfg3/4 u8 CF bicubic STREAM (LDG)", x, (512, 512), "cubic", capi.FLAG_FORCE_STREAM, b)
+    run("cfg3/4 u8 CF bicubic STREAM (TMA)", x, (512, 512), "cubic", capi.FLAG_FORCE_STREAM | capi.FLAG_STREAM_TMA, b)
+    y = capi.resize_forward(x, (512, 512), "cubic", False, capi.FLAG_FORCE_STREAM | capi.FLAG_STREAM_TMA)
+    torch.cuda.synchronize()
+    print("TMA vs LDG max abs diff (u8 cubic)", (y - ref).abs().max().item())
+    del x
