@@ -142,8 +142,7 @@ def cpu_reference_rate(cfg, seconds, torch, threads=None):
     ref = load_ref(build_if_missing=False)
     if ref is None:
         return None
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or len(os.sched_getaffinity(0)))
     cores = torch.get_num_threads()
     ns = 8 if cfg["H"] * cfg["W"] < 3e6 else 2
     g = torch.Generator().manual_seed(0)
@@ -189,6 +188,8 @@ def run_reference(args, cfg, rank, world):
     if ref is None:
         line["unavailable"] = "oracle/_ref (compiled reference) is missing"
         print(json.dumps(line)); return
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host thread it can
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
     cores = torch.get_num_threads()
     ns = 8 if cfg["H"] * cfg["W"] < 3e6 else 2
     g = torch.Generator().manual_seed(0)
