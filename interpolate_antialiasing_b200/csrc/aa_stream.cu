@@ -25,6 +25,9 @@
 // separable sum with fp32 rounding of the intermediate; the difference is pure rounding
 // (measured <= 1.3e-4 abs / 2.3e-6 rel on a 0..255 scale against the reference, tolerance
 // 1e-3 abs / 1e-5 rel -- tests/test_forward_gpu.py).  The bit-exact order lives in aa_general.cu.
+#include <map>
+#include <mutex>
+
 #include "aa_stream_common.cuh"
 
 namespace aa {
@@ -41,21 +44,24 @@ namespace {
 template <int A, int VEC, typename in_t, int NT, int U, int MINB>
 __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int RPT = 4;  // rows per thread in the horizontal phase
+  constexpr int RPT = 4;
+  constexpr int VW = NT * VEC;  // row pitch of Vs in floats (== P.vw)  // rows per thread in the horizontal phase
   constexpr int RS4 = (A + 1 + 3) / 4;  // float4 per slot record
   float* Vs = smem;                                  // [vr][vw]
   float* Ws = Vs + (size_t)P.vr * P.vw;              // [strip_ox][Kw]
   int* sxmin = reinterpret_cast<int*>(Ws + (size_t)P.strip_ox * P.Kw);  // [strip_ox]
   int* sxsize = sxmin + P.strip_ox;                                      // [strip_ox]
+  int2* colinfo = reinterpret_cast<int2*>(sxsize + ((P.strip_ox + 1) & ~1));          // [strip_ox * Ci]
 
   const int t = threadIdx.x;
   const int Ci = P.Ci;
   const int64_t oH = P.oH;
   const int64_t stride_h = P.lin.stride_h;
-  const int vw = P.vw;
+  constexpr int vw = VW;
   const int64_t u_begin = P.total_units * (int64_t)blockIdx.x / gridDim.x;
   const int64_t u_end = P.total_units * (int64_t)(blockIdx.x + 1) / gridDim.x;
-  int cur_strip = -1;
+  int cur_strip = -1, strip_fl0 = 0, strip_nof = 0;
+  HRole role = {0, 1, 0, 1};
 
   for (int64_t u = u_begin; u < u_end;) {
     // ---- segment = run of output rows [oyA, oyB) inside one (plane, strip) column
@@ -74,8 +80,13 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
       for (int i = t; i < nox; i += NT) { sxmin[i] = __ldg(P.xmin_w + ox0 + i); sxsize[i] = __ldg(P.xsize_w + ox0 + i); }
       cur_strip = s;
       __syncthreads();
+      strip_fl0 = (sxmin[0] * Ci) & ~(P.aln - 1);
+      strip_nof = nox * Ci;
+      hphase_build_colinfo(colinfo, sxmin, sxsize, t, NT, strip_nof, Ci, P.Kw, strip_fl0);
+      role = hphase_role(t, NT, strip_nof);
+      __syncthreads();
     }
-    const int fl0 = (sxmin[0] * Ci) & ~(P.aln - 1);                          // first flat element of the strip
+    const int fl0 = strip_fl0;                                                // first flat element of the strip
     const int fl_end = (sxmin[ox1 - ox0 - 1] + sxsize[ox1 - ox0 - 1]) * Ci;  // one past the last
     const bool valid = fl0 + VEC * t < fl_end;
     // threads beyond the strip re-read its first vector (a legal address) and never store
@@ -85,7 +96,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
     const in_t* ip = (const in_t*)P.in + (plane / P.lin.Cp) * P.lin.stride_n + (plane % P.lin.Cp) * P.lin.stride_p + fmy + yA * stride_h;
     const float4* rp = reinterpret_cast<const float4*>(P.slot_h) + yA * RS4;
     float* op = P.out + (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p + (int64_t)ox0 * Ci;
-    const int nof = (ox1 - ox0) * Ci;
+    const int nof = strip_nof;
     float* vdst = Vs + VEC * t;
 
     float acc[A][VEC];
@@ -127,29 +138,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
     // horizontal filter over the buffered rows [gbase, gbase+cnt)
     auto hphase = [&]() {
       __syncthreads();
-      const int nrg = (cnt + RPT - 1) / RPT;
-      for (int item = t; item < nof * nrg; item += NT) {
-        const int rg = item / nof;
-        const int cf = item - rg * nof;  // flat output column inside the strip
-        const int oxl = cf / Ci;
-        const int c = cf - oxl * Ci;
-        const int xs = sxsize[oxl];
-        const float* wr = Ws + oxl * P.Kw;
-        const float* vs = Vs + (size_t)(rg * RPT) * vw + (sxmin[oxl] * Ci + c - fl0);
-        float h[RPT];
-#pragma unroll
-        for (int r = 0; r < RPT; r++) h[r] = 0.f;
-        for (int j = 0; j < xs; j++) {
-          const float wj = wr[j];
-#pragma unroll
-          for (int r = 0; r < RPT; r++) h[r] = fmaf(wj, vs[(size_t)r * vw + j * Ci], h[r]);
-        }
-#pragma unroll
-        for (int r = 0; r < RPT; r++) {
-          const int rowi = rg * RPT + r;
-          if (rowi < cnt) op[(int64_t)(gbase + rowi) * P.lout.stride_h + cf] = h[r];
-        }
-      }
+      hphase_run<RPT, VW>(Vs, Ws, colinfo, op, P.lout.stride_h, Ci, nof, role, gbase, cnt);
       __syncthreads();
       gbase += cnt;
       cnt = 0;
@@ -199,19 +188,26 @@ template <int A, int VEC, typename in_t>
 int launch_cfg(SParams& P, const AxisTables* th, const AxisTables* tw, int device, cudaStream_t stream) {
   using C = Cfg<A, VEC, in_t>;
   auto kern = aa_stream_kernel<A, VEC, in_t, C::NT, C::U, C::MINB>;
-  int rc = plan_stream(P, th, tw, C::NT * VEC, VEC, VEC, C::U, C::TG);
-  if (rc != AA_OK) return rc;
-  const int strip_ox = P.strip_ox;
-  const size_t smem = sizeof(float) * ((size_t)P.vr * P.vw + (size_t)strip_ox * P.Kw) + sizeof(int) * 2 * (size_t)strip_ox;
-  if (smem > 200 * 1024) return fail(AA_ERR_UNSUPPORTED, "stream: shared memory plan too large");
-  AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0, sms = 0;
-  AA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NT, smem));
-  AA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  if (occ < 1) return fail(AA_ERR_UNSUPPORTED, "stream: kernel does not fit on an SM");
-  int64_t grid = (int64_t)occ * sms;
+  const PlanKey key{th, tw, P.Ci, (A << 8) | (VEC << 2) | (int)sizeof(in_t) % 4};
+  Plan pl;
+  if (!plan_lookup(key, &pl)) {
+    P.in_pitch = 0;
+    int rc = plan_stream(P, th, tw, C::NT * VEC, VEC, VEC, C::U, C::TG);
+    if (rc != AA_OK) return rc;
+    const size_t smem_ = sizeof(float) * ((size_t)P.vr * P.vw + (size_t)P.strip_ox * P.Kw) + sizeof(int) * 2 * (size_t)(P.strip_ox + 1) * (1 + P.Ci);
+    if (smem_ > 200 * 1024) return fail(AA_ERR_UNSUPPORTED, "stream: shared memory plan too large");
+    AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int occ = 0, sms = 0;
+    AA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NT, smem_));
+    AA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (occ < 1) return fail(AA_ERR_UNSUPPORTED, "stream: kernel does not fit on an SM");
+    pl = plan_from(P, smem_, occ * sms);
+    plan_store(key, pl);
+  }
+  plan_apply(P, pl);
+  const size_t smem = pl.smem;
   const int64_t min_units = 4;  // do not cut segments shorter than this many output rows
-  grid = std::max<int64_t>(1, std::min<int64_t>(grid, P.total_units / min_units));
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(pl.max_grid, P.total_units / min_units));
   kern<<<(unsigned)grid, C::NT, smem, stream>>>(P);
   AA_LAUNCH_CHECK("aa_stream_kernel");
   return AA_OK;
@@ -229,6 +225,28 @@ int launch_A(SParams& P, int in_dtype, int vec, const AxisTables* th, const Axis
 }
 
 }  // namespace
+
+namespace stream_detail {
+namespace {
+std::mutex g_plan_mu;
+std::map<PlanKey, Plan> g_plans;
+}  // namespace
+bool plan_lookup(const PlanKey& k, Plan* p) {
+  std::lock_guard<std::mutex> lock(g_plan_mu);
+  auto it = g_plans.find(k);
+  if (it == g_plans.end()) return false;
+  *p = it->second;
+  return true;
+}
+void plan_store(const PlanKey& k, const Plan& p) {
+  std::lock_guard<std::mutex> lock(g_plan_mu);
+  g_plans[k] = p;
+}
+void plan_clear() {
+  std::lock_guard<std::mutex> lock(g_plan_mu);
+  g_plans.clear();
+}
+}  // namespace stream_detail
 
 int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout,
                   AxisTables* th, AxisTables* tw, int64_t H, int64_t W, int64_t oH, int64_t oW,

@@ -91,6 +91,76 @@ template <int VEC> __device__ __forceinline__ void store_vec(float* dst, const f
 }
 
 
+// ---- horizontal phase (shared by both variants) ---------------------------------------------
+// Per strip, every flat output column gets a packed descriptor in shared memory so the phase needs no
+// integer division: x = first tap's offset inside a Vs row, y = (offset of the column's weights in
+// Ws) | (window length << 20).
+struct HRole {        // which (row group, column) items a thread owns; fixed per strip
+  int rg0, rg_par;    // first row group and stride over row groups
+  int cf0, cf_step;   // first flat column and stride over columns
+};
+__device__ __forceinline__ HRole hphase_role(int t, int nthreads, int nof) {
+  HRole r;
+  const int nw = nthreads >> 5, warp = t >> 5, lane = t & 31;
+  const int wpr = (nof + 31) >> 5;  // warps needed to cover one row group
+  if (wpr >= nw) { r.rg0 = 0; r.rg_par = 1; r.cf0 = t; r.cf_step = nthreads; }
+  else {
+    r.rg_par = nw / wpr;
+    r.rg0 = warp / wpr;
+    if (r.rg0 >= r.rg_par) r.rg0 = 1 << 20;  // idle warp
+    r.cf0 = (warp - (warp / wpr) * wpr) * 32 + lane;
+    r.cf_step = wpr * 32;
+  }
+  return r;
+}
+__device__ __forceinline__ void hphase_build_colinfo(int2* colinfo, const int* sxmin, const int* sxsize, int t, int nthreads,
+                                                     int nof, int Ci, int Kw, int fl0) {
+  for (int cf = t; cf < nof; cf += nthreads) {
+    const int oxl = cf / Ci;
+    const int c = cf - oxl * Ci;
+    colinfo[cf] = make_int2(sxmin[oxl] * Ci + c - fl0, (oxl * Kw) | (sxsize[oxl] << 20));
+  }
+}
+// Gather over the buffered rows [0, cnt) of Vs -> output rows gbase..gbase+cnt-1.  Trip counts are
+// warp-uniform (max window length in the warp) with per-lane predication, so there is no divergence and
+// no tap outside a column's true window is ever read.
+template <int RPT, int VW>
+__device__ __forceinline__ void hphase_run(const float* __restrict__ Vs, const float* __restrict__ Ws,
+                                           const int2* __restrict__ colinfo, float* __restrict__ op, int64_t out_stride_h,
+                                           int Ci, int nof, const HRole role, int gbase, int cnt) {
+  const int nrg = (cnt + RPT - 1) / RPT;
+  for (int rg = role.rg0; rg < nrg; rg += role.rg_par) {
+    for (int cfb = role.cf0 - (role.cf0 & 31); cfb < nof; cfb += role.cf_step) {
+      const int cf = cfb + (role.cf0 & 31);
+      const bool act = cf < nof;
+      const int2 ci = colinfo[act ? cf : 0];
+      const int xs = act ? (ci.y >> 20) : 1;
+      const int xsm = __reduce_max_sync(0xffffffffu, xs);
+      const float* wr = Ws + (ci.y & 0xfffff);
+      const float* vp = Vs + (rg * RPT) * VW + ci.x;
+      float h[RPT];
+#pragma unroll
+      for (int r = 0; r < RPT; r++) h[r] = 0.f;
+      // Warp-uniform trip count.  Past a lane's own window the weight read is the table's zero padding
+      // (aa_interpolation_impl.h:276-278) and the data pointer stops advancing, so no element outside
+      // the true window is touched.
+#pragma unroll 4
+      for (int j = 0; j < xsm; j++) {
+        const float wj = wr[j];
+#pragma unroll
+        for (int r = 0; r < RPT; r++) h[r] = fmaf(wj, vp[r * VW], h[r]);
+        vp += (j + 1 < xs) ? Ci : 0;
+      }
+      if (act) {
+        float* dst = op + (int64_t)(gbase + rg * RPT) * out_stride_h + cf;
+#pragma unroll
+        for (int r = 0; r < RPT; r++)
+          if (rg * RPT + r < cnt) dst[(int64_t)r * out_stride_h] = h[r];
+      }
+    }
+  }
+}
+
 // Strip / row-buffer plan shared by both variants (exact, from the host mirrors of the tables).
 //   cap   flat elements one strip may span (threads * VEC)
 //   aln   alignment of a strip's first element (VEC, or 16 bytes' worth for the TMA variant)
@@ -118,8 +188,8 @@ inline int plan_stream(SParams& P, const AxisTables* th, const AxisTables* tw, i
   P.n_strips = n_strips;
   P.strip_ox = strip_ox;
   P.aln = aln;
-  const int va = std::max(std::max(vec, 4), aln);
-  P.vw = (int)((max_extent + va - 1) / va * va);
+  (void)vec;
+  P.vw = cap;  // compile-time row pitch of Vs (lets the horizontal phase use immediate row offsets)
   int fmax = 1;
   {
     const int64_t oH = P.oH;
@@ -135,6 +205,35 @@ inline int plan_stream(SParams& P, const AxisTables* th, const AxisTables* tw, i
   if (P.vr > 32) return fail(AA_ERR_UNSUPPORTED, "stream: too many output rows finish per input batch (upsampling in H)");
   P.total_units = P.lin.planes * n_strips * P.oH;
   return AA_OK;
+}
+
+// Launch plans are cached per (tables, interleave, kernel variant): the steady-state host cost of a
+// call is one map lookup + one kernel launch (no occupancy queries, no attribute calls).
+struct PlanKey {
+  const void *th, *tw;
+  int Ci, kid;
+  bool operator<(const PlanKey& o) const {
+    if (th != o.th) return th < o.th;
+    if (tw != o.tw) return tw < o.tw;
+    if (Ci != o.Ci) return Ci < o.Ci;
+    return kid < o.kid;
+  }
+};
+struct Plan {
+  int n_strips, strip_ox, vw, vr, tg, aln, in_pitch;
+  size_t smem;
+  int max_grid;  // SMs * resident CTAs per SM
+};
+bool plan_lookup(const PlanKey& k, Plan* p);
+void plan_store(const PlanKey& k, const Plan& p);
+void plan_clear();
+inline void plan_apply(SParams& P, const Plan& pl) {
+  P.n_strips = pl.n_strips; P.strip_ox = pl.strip_ox; P.vw = pl.vw; P.vr = pl.vr; P.tg = pl.tg; P.aln = pl.aln;
+  P.in_pitch = pl.in_pitch;
+  P.total_units = P.lin.planes * pl.n_strips * P.oH;
+}
+inline Plan plan_from(const SParams& P, size_t smem, int max_grid) {
+  return Plan{P.n_strips, P.strip_ox, P.vw, P.vr, P.tg, P.aln, P.in_pitch, smem, max_grid};
 }
 
 }  // namespace stream_detail

@@ -69,6 +69,7 @@ template <int A, int VEC, typename in_t, int R, int STAGES, int MINB>
 __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int RPT = 4;
+  constexpr int VW = NTC * VEC;  // row pitch of Vs in floats (== P.vw)
   constexpr int RS4 = (A + 1 + 3) / 4;
   constexpr int ES = (int)sizeof(in_t);
   // layout: [stages][R][in_pitch] staged input | Vs[vr][vw] | Ws[strip_ox][Kw] | sxmin | sxsize | mbarriers
@@ -77,7 +78,8 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
   float* Ws = Vs + (size_t)P.vr * P.vw;
   int* sxmin = reinterpret_cast<int*>(Ws + (size_t)P.strip_ox * P.Kw);
   int* sxsize = sxmin + P.strip_ox;
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sxsize + P.strip_ox) + 7) & ~(uintptr_t)7);
+  int2* colinfo = reinterpret_cast<int2*>(sxsize + ((P.strip_ox + 1) & ~1));  // [strip_ox * Ci]
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(colinfo + (size_t)P.strip_ox * P.Ci) + 7) & ~(uintptr_t)7);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
 
   const int t = threadIdx.x;
@@ -130,8 +132,9 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
   }
 
   // =============================== consumers ========================================================
-  const int vw = P.vw;
-  int cur_strip = -1;
+  constexpr int vw = VW;
+  int cur_strip = -1, strip_fl0 = 0, strip_nof = 0;
+  HRole role = {0, 1, 0, 1};
   for (int64_t u = u_begin; u < u_end;) {
     const int64_t col = u / oH;
     const int oyA = (int)(u - col * oH);
@@ -148,15 +151,20 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
       for (int i = t; i < nox; i += NTC) { sxmin[i] = __ldg(P.xmin_w + ox0 + i); sxsize[i] = __ldg(P.xsize_w + ox0 + i); }
       cur_strip = s;
       consumer_sync();
+      strip_fl0 = (sxmin[0] * Ci) & ~(P.aln - 1);
+      strip_nof = nox * Ci;
+      hphase_build_colinfo(colinfo, sxmin, sxsize, t, NTC, strip_nof, Ci, P.Kw, strip_fl0);
+      role = hphase_role(t, NTC, strip_nof);
+      consumer_sync();
     }
-    const int fl0 = (sxmin[0] * Ci) & ~(P.aln - 1);
-    const int fl_end = (sxmin[ox1 - ox0 - 1] + sxsize[ox1 - ox0 - 1]) * Ci;
+    const int fl0 = strip_fl0;                                                // first flat element of the strip
+    const int fl_end = (sxmin[ox1 - ox0 - 1] + sxsize[ox1 - ox0 - 1]) * Ci;  // one past the last
     const bool valid = fl0 + VEC * t < fl_end;
     const int64_t yA = __ldg(P.xmin_h + oyA);
     const int64_t yB = (int64_t)__ldg(P.xmin_h + oyB - 1) + __ldg(P.xsize_h + oyB - 1);
     const float4* rp = reinterpret_cast<const float4*>(P.slot_h) + yA * RS4;
     float* op = P.out + (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p + (int64_t)ox0 * Ci;
-    const int nof = (ox1 - ox0) * Ci;
+    const int nof = strip_nof;
     float* vdst = Vs + VEC * t;
     const unsigned char* my_in = stage_base + (size_t)VEC * ES * t;  // + stage*R*in_pitch + i*in_pitch
 
@@ -195,29 +203,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
     };
     auto hphase = [&]() {
       consumer_sync();
-      const int nrg = (cnt + RPT - 1) / RPT;
-      for (int item = t; item < nof * nrg; item += NTC) {
-        const int rg = item / nof;
-        const int cf = item - rg * nof;
-        const int oxl = cf / Ci;
-        const int c = cf - oxl * Ci;
-        const int xs = sxsize[oxl];
-        const float* wr = Ws + oxl * P.Kw;
-        const float* vs = Vs + (size_t)(rg * RPT) * vw + (sxmin[oxl] * Ci + c - fl0);
-        float h[RPT];
-#pragma unroll
-        for (int r = 0; r < RPT; r++) h[r] = 0.f;
-        for (int j = 0; j < xs; j++) {
-          const float wj = wr[j];
-#pragma unroll
-          for (int r = 0; r < RPT; r++) h[r] = fmaf(wj, vs[(size_t)r * vw + j * Ci], h[r]);
-        }
-#pragma unroll
-        for (int r = 0; r < RPT; r++) {
-          const int rowi = rg * RPT + r;
-          if (rowi < cnt) op[(int64_t)(gbase + rowi) * P.lout.stride_h + cf] = h[r];
-        }
-      }
+      hphase_run<RPT, VW>(Vs, Ws, colinfo, op, P.lout.stride_h, Ci, nof, role, gbase, cnt);
       consumer_sync();
       gbase += cnt;
       cnt = 0;
@@ -266,19 +252,26 @@ int launch_tma_cfg(SParams& P, const AxisTables* th, const AxisTables* tw, int d
   constexpr int MINB = 2;
   constexpr int ES = (int)sizeof(in_t);
   auto kern = aa_stream_tma_kernel<A, VEC, in_t, R, STAGES, MINB>;
-  int rc = plan_stream(P, th, tw, NTC * VEC, 16 / ES, VEC, R, 4);
-  if (rc != AA_OK) return rc;
-  P.in_pitch = (P.vw * ES + 15) & ~15;
-  const size_t smem = (size_t)STAGES * R * P.in_pitch + sizeof(float) * ((size_t)P.vr * P.vw + (size_t)P.strip_ox * P.Kw) +
-                      sizeof(int) * 2 * (size_t)P.strip_ox + 8 + 16 * STAGES;
-  if (smem > 200 * 1024) return fail(AA_ERR_UNSUPPORTED, "stream/tma: shared memory plan too large");
-  AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0, sms = 0;
-  AA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
-  AA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  if (occ < 1) return fail(AA_ERR_UNSUPPORTED, "stream/tma: kernel does not fit on an SM");
-  int64_t grid = (int64_t)occ * sms;
-  grid = std::max<int64_t>(1, std::min<int64_t>(grid, P.total_units / 4));
+  const PlanKey key{th, tw, P.Ci, 0x10000 | (A << 8) | (VEC << 2) | ES % 4};
+  Plan pl;
+  if (!plan_lookup(key, &pl)) {
+    int rc = plan_stream(P, th, tw, NTC * VEC, 16 / ES, VEC, R, 4);
+    if (rc != AA_OK) return rc;
+    P.in_pitch = (P.vw * ES + 15) & ~15;
+    const size_t smem_ = (size_t)STAGES * R * P.in_pitch + sizeof(float) * ((size_t)P.vr * P.vw + (size_t)P.strip_ox * P.Kw) +
+                         sizeof(int) * 2 * (size_t)(P.strip_ox + 1) * (1 + P.Ci) + 8 + 16 * STAGES;
+    if (smem_ > 200 * 1024) return fail(AA_ERR_UNSUPPORTED, "stream/tma: shared memory plan too large");
+    AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int occ = 0, sms = 0;
+    AA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem_));
+    AA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (occ < 1) return fail(AA_ERR_UNSUPPORTED, "stream/tma: kernel does not fit on an SM");
+    pl = plan_from(P, smem_, occ * sms);
+    plan_store(key, pl);
+  }
+  plan_apply(P, pl);
+  const size_t smem = pl.smem;
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(pl.max_grid, P.total_units / 4));
   kern<<<(unsigned)grid, NT, smem, stream>>>(P);
   AA_LAUNCH_CHECK("aa_stream_tma_kernel");
   return AA_OK;

@@ -392,7 +392,10 @@ int ensure_slot_tables(AxisTables* t, int A, cudaStream_t stream) {
   return AA_OK;
 }
 
+namespace stream_detail { void plan_clear(); }
+
 int clear_table_cache() {
+  stream_detail::plan_clear();
   std::lock_guard<std::mutex> lock(g_mu);
   g_cache.clear();
   return AA_OK;
