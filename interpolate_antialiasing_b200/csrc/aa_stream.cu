@@ -47,11 +47,11 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
   constexpr int RPT = 4;
   constexpr int VW = NT * VEC;  // row pitch of Vs in floats (== P.vw)  // rows per thread in the horizontal phase
   constexpr int RS4 = (A + 1 + 3) / 4;  // float4 per slot record
+  using RawT = typename Raw<in_t, VEC>::T;
+  constexpr int RN = Raw<in_t, VEC>::N;
   float* Vs = smem;                                  // [vr][vw]
-  float* Ws = Vs + (size_t)P.vr * P.vw;              // [strip_ox][Kw]
-  int* sxmin = reinterpret_cast<int*>(Ws + (size_t)P.strip_ox * P.Kw);  // [strip_ox]
-  int* sxsize = sxmin + P.strip_ox;                                      // [strip_ox]
-  int2* colinfo = reinterpret_cast<int2*>(sxsize + ((P.strip_ox + 1) & ~1));          // [strip_ox * Ci]
+  float2* Wp = reinterpret_cast<float2*>(Vs + (size_t)P.vr * P.vw);                       // [pairs][kp]
+  int4* pinfo = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(Wp) + P.wtab_bytes + 15) & ~(uintptr_t)15);      // [pairs * Ci]
 
   const int t = threadIdx.x;
   const int Ci = P.Ci;
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
   constexpr int vw = VW;
   const int64_t u_begin = P.total_units * (int64_t)blockIdx.x / gridDim.x;
   const int64_t u_end = P.total_units * (int64_t)(blockIdx.x + 1) / gridDim.x;
-  int cur_strip = -1, strip_fl0 = 0, strip_nof = 0;
+  int cur_strip = -1, strip_fl0 = 0, strip_npc = 0;
   HRole role = {0, 1, 0, 1};
 
   for (int64_t u = u_begin; u < u_end;) {
@@ -75,19 +75,13 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
     const int ox1 = min((int)P.oW, ox0 + P.strip_ox);
     if (s != cur_strip) {
       __syncthreads();
-      const int nox = ox1 - ox0;
-      for (int i = t; i < nox * P.Kw; i += NT) Ws[i] = __ldg(P.w_w + (int64_t)ox0 * P.Kw + i);
-      for (int i = t; i < nox; i += NT) { sxmin[i] = __ldg(P.xmin_w + ox0 + i); sxsize[i] = __ldg(P.xsize_w + ox0 + i); }
+      strip_setup(P, t, NT, ox0, ox1, Wp, pinfo, &strip_fl0, &strip_npc);
+      role = hphase_role(t, NT, strip_npc);
       cur_strip = s;
       __syncthreads();
-      strip_fl0 = (sxmin[0] * Ci) & ~(P.aln - 1);
-      strip_nof = nox * Ci;
-      hphase_build_colinfo(colinfo, sxmin, sxsize, t, NT, strip_nof, Ci, P.Kw, strip_fl0);
-      role = hphase_role(t, NT, strip_nof);
-      __syncthreads();
     }
-    const int fl0 = strip_fl0;                                                // first flat element of the strip
-    const int fl_end = (sxmin[ox1 - ox0 - 1] + sxsize[ox1 - ox0 - 1]) * Ci;  // one past the last
+    const int fl0 = strip_fl0;                                                              // first flat element of the strip
+    const int fl_end = (__ldg(P.xmin_w + ox1 - 1) + __ldg(P.xsize_w + ox1 - 1)) * Ci;       // one past the last
     const bool valid = fl0 + VEC * t < fl_end;
     // threads beyond the strip re-read its first vector (a legal address) and never store
     const int fmy = valid ? fl0 + VEC * t : fl0;
@@ -96,7 +90,6 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
     const in_t* ip = (const in_t*)P.in + (plane / P.lin.Cp) * P.lin.stride_n + (plane % P.lin.Cp) * P.lin.stride_p + fmy + yA * stride_h;
     const float4* rp = reinterpret_cast<const float4*>(P.slot_h) + yA * RS4;
     float* op = P.out + (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p + (int64_t)ox0 * Ci;
-    const int nof = strip_nof;
     float* vdst = Vs + VEC * t;
 
     float acc[A][VEC];
@@ -110,12 +103,11 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
     // one input row: A FMAs per element with warp-uniform weights; acc[k] belongs to the k-th oldest
     // open output row.  When rows finish (rarely: once per scale_h rows) the oldest accumulators are
     // stored to shared memory and the rest shift down.
-    auto row = [&](const float (&v)[VEC], const float4 (&rq)[RS4]) {
+    auto row = [&](const RawT (&raw)[RN], const float4 (&rq)[RS4]) {
       const float* rw = reinterpret_cast<const float*>(rq);
-#pragma unroll
-      for (int a = 0; a < A; a++)
-#pragma unroll
-        for (int e = 0; e < VEC; e++) acc[a][e] = fmaf(rw[a], v[e], acc[a][e]);
+      float v[VEC];
+      expand<VEC>(raw, v);
+      vfma<A, VEC>(acc, v, rw);
       const int packed = __float_as_int(rw[A]);
       if (packed >> 24) {
         const int nfl = packed >> 24;
@@ -138,7 +130,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
     // horizontal filter over the buffered rows [gbase, gbase+cnt)
     auto hphase = [&]() {
       __syncthreads();
-      hphase_run<RPT, VW>(Vs, Ws, colinfo, op, P.lout.stride_h, Ci, nof, role, gbase, cnt);
+      hphase_run<RPT, VW>(P, Vs, Wp, pinfo, op, strip_npc, role, gbase, cnt);
       __syncthreads();
       gbase += cnt;
       cnt = 0;
@@ -146,7 +138,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
 
     int64_t y = yA;
     for (; y + U <= yB; y += U) {
-      float v[U][VEC];
+      RawT v[U][RN];
       float4 rq[U][RS4];
 #pragma unroll
       for (int i = 0; i < U; i++) VLoad<in_t, VEC>::ld(ip + i * stride_h, v[i]);
@@ -161,7 +153,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
       if (cnt >= P.tg) hphase();
     }
     for (; y < yB; y++) {
-      float v[VEC];
+      RawT v[RN];
       float4 rq[RS4];
       VLoad<in_t, VEC>::ld(ip, v);
 #pragma unroll
@@ -181,7 +173,7 @@ struct Cfg {
   static constexpr int U = 4;
   static constexpr int TG = 4;  // buffered rows that trigger a horizontal phase
   // register budget: 64/thread (4 CTAs/SM) when the accumulators are few, else 2-3 CTAs/SM
-  static constexpr int MINB = (A * VEC <= 12) ? 4 : ((A * VEC <= 24) ? 3 : 2);
+  static constexpr int MINB = (A * VEC <= 12) ? 4 : ((A * VEC <= 32) ? 3 : 2);
 };
 
 template <int A, int VEC, typename in_t>
@@ -194,7 +186,7 @@ int launch_cfg(SParams& P, const AxisTables* th, const AxisTables* tw, int devic
     P.in_pitch = 0;
     int rc = plan_stream(P, th, tw, C::NT * VEC, VEC, VEC, C::U, C::TG);
     if (rc != AA_OK) return rc;
-    const size_t smem_ = sizeof(float) * ((size_t)P.vr * P.vw + (size_t)P.strip_ox * P.Kw) + sizeof(int) * 2 * (size_t)(P.strip_ox + 1) * (1 + P.Ci);
+    const size_t smem_ = sizeof(float) * (size_t)P.vr * P.vw + strip_table_bytes(P);
     if (smem_ > 200 * 1024) return fail(AA_ERR_UNSUPPORTED, "stream: shared memory plan too large");
     AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int occ = 0, sms = 0;

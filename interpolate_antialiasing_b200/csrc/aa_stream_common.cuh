@@ -29,9 +29,18 @@ struct SParams {
   int tg;               // buffered rows that trigger a horizontal phase
   int aln;              // alignment (elements) of a strip's first flat element
   int in_pitch;         // TMA variant: bytes between staged input rows in shared memory
+  int kp;               // pitch of the paired weight table = Kw + max(xmin[o+1]-xmin[o]) over pairs
+  int pairs;            // horizontal phase computes pairs of adjacent output columns (wide strips)
+  int wtab_bytes;       // bytes reserved for the weight table (pinfo follows, 16-byte aligned)
 };
 
 // ---- vector loads (read-once data: bypass L1 allocation) -------------------------------------
+// Loads return RAW registers (floats, or packed bytes for uint8 input); expand() turns them into
+// floats right before the FMAs, so a batch of U rows in flight costs U*VEC/4 registers for uint8.
+template <typename in_t, int VEC> struct Raw;
+template <int VEC> struct Raw<float, VEC> { static constexpr int N = VEC; using T = float; };
+template <int VEC> struct Raw<uint8_t, VEC> { static constexpr int N = VEC / 4; using T = uint32_t; };
+
 template <typename in_t, int VEC> struct VLoad;
 template <> struct VLoad<float, 4> {
   static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
@@ -49,33 +58,60 @@ template <> struct VLoad<float, 1> {
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v[0]) : "l"(p));
   }
 };
-__device__ __forceinline__ void unpack4(uint32_t w, float* v) {
-  v[0] = (float)(w & 0xffu);
-  v[1] = (float)((w >> 8) & 0xffu);
-  v[2] = (float)((w >> 16) & 0xffu);
-  v[3] = (float)(w >> 24);
-}
 template <> struct VLoad<uint8_t, 16> {
-  static __device__ __forceinline__ void ld(const uint8_t* p, float (&v)[16]) {
-    uint32_t a, b, c, d;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
-    unpack4(a, v); unpack4(b, v + 4); unpack4(c, v + 8); unpack4(d, v + 12);
+  static __device__ __forceinline__ void ld(const uint8_t* p, uint32_t (&r)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
   }
 };
 template <> struct VLoad<uint8_t, 8> {
-  static __device__ __forceinline__ void ld(const uint8_t* p, float (&v)[8]) {
-    uint32_t a, b;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
-    unpack4(a, v); unpack4(b, v + 4);
+  static __device__ __forceinline__ void ld(const uint8_t* p, uint32_t (&r)[2]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "l"(p));
   }
 };
 template <> struct VLoad<uint8_t, 4> {
-  static __device__ __forceinline__ void ld(const uint8_t* p, float (&v)[4]) {
-    uint32_t a;
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(a) : "l"(p));
-    unpack4(a, v);
+  static __device__ __forceinline__ void ld(const uint8_t* p, uint32_t (&r)[1]) {
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r[0]) : "l"(p));
   }
 };
+// uint8 -> float without the conversion unit (I2F runs on the 16-lane XU pipe): PRMT drops the byte
+// into the mantissa of 2^23 (0x4B0000bb == 8388608 + b exactly) and one FADD removes the bias.
+__device__ __forceinline__ void unpack4(uint32_t w, float* v) {
+  v[0] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)) - 8388608.0f;
+  v[1] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541)) - 8388608.0f;
+  v[2] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)) - 8388608.0f;
+  v[3] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543)) - 8388608.0f;
+}
+template <int VEC> __device__ __forceinline__ void expand(const float (&r)[VEC], float (&v)[VEC]) {
+#pragma unroll
+  for (int i = 0; i < VEC; i++) v[i] = r[i];
+}
+template <int VEC> __device__ __forceinline__ void expand(const uint32_t (&r)[VEC / 4], float (&v)[VEC]) {
+#pragma unroll
+  for (int i = 0; i < VEC / 4; i++) unpack4(r[i], v + 4 * i);
+}
+
+// acc[a][:] += w[a] * v[:] for the A open output rows; packed FFMA2 (two fp32 FMAs per issue slot,
+// scalar weight broadcast) whenever the thread owns an even number of elements.
+template <int A, int VEC>
+__device__ __forceinline__ void vfma(float (&acc)[A][VEC], const float (&v)[VEC], const float* rw) {
+  if constexpr (VEC % 2 == 0) {
+#pragma unroll
+    for (int a = 0; a < A; a++) {
+      const float2 w2 = make_float2(rw[a], rw[a]);
+#pragma unroll
+      for (int e = 0; e < VEC; e += 2) {
+        const float2 r = __ffma2_rn(w2, make_float2(v[e], v[e + 1]), make_float2(acc[a][e], acc[a][e + 1]));
+        acc[a][e] = r.x;
+        acc[a][e + 1] = r.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < A; a++)
+#pragma unroll
+      for (int e = 0; e < VEC; e++) acc[a][e] = fmaf(rw[a], v[e], acc[a][e]);
+  }
+}
 
 template <int VEC> __device__ __forceinline__ void store_vec(float* dst, const float* a) {
   if constexpr (VEC % 4 == 0) {
@@ -92,17 +128,21 @@ template <int VEC> __device__ __forceinline__ void store_vec(float* dst, const f
 
 
 // ---- horizontal phase (shared by both variants) ---------------------------------------------
-// Per strip, every flat output column gets a packed descriptor in shared memory so the phase needs no
-// integer division: x = first tap's offset inside a Vs row, y = (offset of the column's weights in
-// Ws) | (window length << 20).
-struct HRole {        // which (row group, column) items a thread owns; fixed per strip
+// Adjacent output columns have heavily overlapping windows (stride scale_w, length 2*support_w), so a
+// thread computes a PAIR of adjacent columns (same channel) for RPT buffered rows: every Vs element it
+// loads feeds both columns, and the two weights arrive in one 64-bit load.  Per strip the kernel builds
+//   Wp[pair][KP]     float2 {w_a[j], w_b[j - shift]} zero padded, shift = xmin_b - xmin_a
+//   pinfo[pair*Ci+c] int4   {first tap's offset in a Vs row, pair*KP, union window length | has_b<<16,
+//                            flat output column of column a}
+// so the phase itself needs no integer division and no per-column table lookups.
+struct HRole {        // which (row group, pair-column) items a thread owns; fixed per strip
   int rg0, rg_par;    // first row group and stride over row groups
-  int cf0, cf_step;   // first flat column and stride over columns
+  int cf0, cf_step;   // first pair-column and stride over pair-columns
 };
-__device__ __forceinline__ HRole hphase_role(int t, int nthreads, int nof) {
+__device__ __forceinline__ HRole hphase_role(int t, int nthreads, int npc) {
   HRole r;
   const int nw = nthreads >> 5, warp = t >> 5, lane = t & 31;
-  const int wpr = (nof + 31) >> 5;  // warps needed to cover one row group
+  const int wpr = (npc + 31) >> 5;  // warps needed to cover one row group
   if (wpr >= nw) { r.rg0 = 0; r.rg_par = 1; r.cf0 = t; r.cf_step = nthreads; }
   else {
     r.rg_par = nw / wpr;
@@ -113,42 +153,119 @@ __device__ __forceinline__ HRole hphase_role(int t, int nthreads, int nof) {
   }
   return r;
 }
-__device__ __forceinline__ void hphase_build_colinfo(int2* colinfo, const int* sxmin, const int* sxsize, int t, int nthreads,
-                                                     int nof, int Ci, int Kw, int fl0) {
-  for (int cf = t; cf < nof; cf += nthreads) {
-    const int oxl = cf / Ci;
-    const int c = cf - oxl * Ci;
-    colinfo[cf] = make_int2(sxmin[oxl] * Ci + c - fl0, (oxl * Kw) | (sxsize[oxl] << 20));
+// Called by all `nthreads` threads between two barriers when the CTA moves to a new strip.
+// P.pairs == 0 builds the single-column form of the same tables instead (narrow strips, where halving
+// the number of independent items would starve the phase): Wp is then a float array with pitch Kw.
+__device__ __forceinline__ void strip_setup(const SParams& P, int t, int nthreads, int ox0, int ox1, float2* Wp, int4* pinfo,
+                                            int* fl0_out, int* npc_out) {
+  const int Ci = P.Ci, Kw = P.Kw, KP = P.kp;
+  const int nox = ox1 - ox0;
+  const int fl0 = (__ldg(P.xmin_w + ox0) * Ci) & ~(P.aln - 1);
+  *fl0_out = fl0;
+  if (!P.pairs) {
+    float* Ws = reinterpret_cast<float*>(Wp);
+    for (int i = t; i < nox * Kw; i += nthreads) Ws[i] = __ldg(P.w_w + (int64_t)ox0 * Kw + i);
+    for (int cf = t; cf < nox * Ci; cf += nthreads) {
+      const int oxl = cf / Ci, c = cf - oxl * Ci;
+      pinfo[cf] = make_int4(__ldg(P.xmin_w + ox0 + oxl) * Ci + c - fl0, oxl * Kw, __ldg(P.xsize_w + ox0 + oxl), cf);
+    }
+    *npc_out = nox * Ci;
+    return;
   }
+  const int np = (nox + 1) >> 1;
+  for (int i = t; i < np * KP; i += nthreads) {
+    const int p = i / KP, j = i - p * KP;
+    const int oa = ox0 + 2 * p, ob = oa + 1;
+    const int xa = __ldg(P.xmin_w + oa), sa = __ldg(P.xsize_w + oa);
+    float wa = j < sa ? __ldg(P.w_w + (int64_t)oa * Kw + j) : 0.f, wb = 0.f;
+    if (ob < ox1) {
+      const int jb = j - (__ldg(P.xmin_w + ob) - xa);
+      if (jb >= 0 && jb < __ldg(P.xsize_w + ob)) wb = __ldg(P.w_w + (int64_t)ob * Kw + jb);
+    }
+    Wp[i] = make_float2(wa, wb);
+  }
+  for (int pc = t; pc < np * Ci; pc += nthreads) {
+    const int p = pc / Ci, c = pc - p * Ci;
+    const int oa = ox0 + 2 * p, ob = oa + 1;
+    const int xa = __ldg(P.xmin_w + oa);
+    int len = __ldg(P.xsize_w + oa), hasb = 0;
+    if (ob < ox1) { len = max(len, __ldg(P.xmin_w + ob) - xa + __ldg(P.xsize_w + ob)); hasb = 1; }
+    pinfo[pc] = make_int4(xa * Ci + c - fl0, p * KP, len | (hasb << 16), 2 * p * Ci + c);
+  }
+  *npc_out = np * Ci;
 }
 // Gather over the buffered rows [0, cnt) of Vs -> output rows gbase..gbase+cnt-1.  Trip counts are
-// warp-uniform (max window length in the warp) with per-lane predication, so there is no divergence and
-// no tap outside a column's true window is ever read.
+// warp-uniform (longest union window in the warp); past a lane's own window the weights read are the
+// zero padding and the data pointer stops advancing, so no element outside the true windows is touched.
 template <int RPT, int VW>
-__device__ __forceinline__ void hphase_run(const float* __restrict__ Vs, const float* __restrict__ Ws,
-                                           const int2* __restrict__ colinfo, float* __restrict__ op, int64_t out_stride_h,
-                                           int Ci, int nof, const HRole role, int gbase, int cnt) {
+__device__ __forceinline__ void hphase_run_pairs(const float* __restrict__ Vs, const float2* __restrict__ Wp,
+                                           const int4* __restrict__ pinfo, float* __restrict__ op, int64_t out_stride_h,
+                                           int Ci, int npc, const HRole role, int gbase, int cnt) {
+  const int nrg = (cnt + RPT - 1) / RPT;
+  for (int rg = role.rg0; rg < nrg; rg += role.rg_par) {
+    for (int cfb = role.cf0 - (role.cf0 & 31); cfb < npc; cfb += role.cf_step) {
+      const int pc = cfb + (role.cf0 & 31);
+      const bool act = pc < npc;
+      const int4 pi = pinfo[act ? pc : 0];
+      const int len = act ? (pi.z & 0xffff) : 1;
+      const int lenm = __reduce_max_sync(0xffffffffu, len);
+      const float2* wr = Wp + pi.y;
+      const float* vp = Vs + (rg * RPT) * VW + pi.x;
+      float2 h[RPT];
+#pragma unroll
+      for (int r = 0; r < RPT; r++) h[r] = make_float2(0.f, 0.f);
+#pragma unroll 4
+      for (int j = 0; j < lenm; j++) {
+        const float2 w2 = wr[j];
+#pragma unroll
+        for (int r = 0; r < RPT; r++) {
+          const float v = vp[r * VW];
+          h[r] = __ffma2_rn(make_float2(v, v), w2, h[r]);
+        }
+        vp += (j + 1 < len) ? Ci : 0;
+      }
+      if (act) {
+        float* dst = op + (int64_t)(gbase + rg * RPT) * out_stride_h + pi.w;
+        const bool hasb = (pi.z >> 16) != 0;
+#pragma unroll
+        for (int r = 0; r < RPT; r++) {
+          if (rg * RPT + r < cnt) {
+            dst[(int64_t)r * out_stride_h] = h[r].x;
+            if (hasb) dst[(int64_t)r * out_stride_h + Ci] = h[r].y;
+          }
+        }
+      }
+    }
+  }
+}
+// single-column form (P.pairs == 0): one item = one flat output column x RPT rows, FFMA2 over row pairs
+template <int RPT, int VW>
+__device__ __forceinline__ void hphase_run_single(const float* __restrict__ Vs, const float* __restrict__ Ws,
+                                                  const int4* __restrict__ pinfo, float* __restrict__ op, int64_t out_stride_h,
+                                                  int Ci, int nof, const HRole role, int gbase, int cnt) {
   const int nrg = (cnt + RPT - 1) / RPT;
   for (int rg = role.rg0; rg < nrg; rg += role.rg_par) {
     for (int cfb = role.cf0 - (role.cf0 & 31); cfb < nof; cfb += role.cf_step) {
       const int cf = cfb + (role.cf0 & 31);
       const bool act = cf < nof;
-      const int2 ci = colinfo[act ? cf : 0];
-      const int xs = act ? (ci.y >> 20) : 1;
+      const int4 ci = pinfo[act ? cf : 0];
+      const int xs = act ? ci.z : 1;
       const int xsm = __reduce_max_sync(0xffffffffu, xs);
-      const float* wr = Ws + (ci.y & 0xfffff);
+      const float* wr = Ws + ci.y;
       const float* vp = Vs + (rg * RPT) * VW + ci.x;
       float h[RPT];
 #pragma unroll
       for (int r = 0; r < RPT; r++) h[r] = 0.f;
-      // Warp-uniform trip count.  Past a lane's own window the weight read is the table's zero padding
-      // (aa_interpolation_impl.h:276-278) and the data pointer stops advancing, so no element outside
-      // the true window is touched.
 #pragma unroll 4
       for (int j = 0; j < xsm; j++) {
         const float wj = wr[j];
+        const float2 w2 = make_float2(wj, wj);
 #pragma unroll
-        for (int r = 0; r < RPT; r++) h[r] = fmaf(wj, vp[r * VW], h[r]);
+        for (int r = 0; r < RPT; r += 2) {
+          const float2 q = __ffma2_rn(w2, make_float2(vp[r * VW], vp[(r + 1) * VW]), make_float2(h[r], h[r + 1]));
+          h[r] = q.x;
+          h[r + 1] = q.y;
+        }
         vp += (j + 1 < xs) ? Ci : 0;
       }
       if (act) {
@@ -159,6 +276,17 @@ __device__ __forceinline__ void hphase_run(const float* __restrict__ Vs, const f
       }
     }
   }
+}
+template <int RPT, int VW>
+__device__ __forceinline__ void hphase_run(const SParams& P, const float* Vs, const float2* Wp, const int4* pinfo, float* op,
+                                           int npc, const HRole role, int gbase, int cnt) {
+  if (P.pairs) hphase_run_pairs<RPT, VW>(Vs, Wp, pinfo, op, P.lout.stride_h, P.Ci, npc, role, gbase, cnt);
+  else hphase_run_single<RPT, VW>(Vs, reinterpret_cast<const float*>(Wp), pinfo, op, P.lout.stride_h, P.Ci, npc, role, gbase, cnt);
+}
+// bytes of the strip tables (after Vs) for a plan
+inline size_t strip_table_bytes(const SParams& P) {
+  const size_t items = P.pairs ? (size_t)((P.strip_ox + 1) / 2) * P.Ci : (size_t)P.strip_ox * P.Ci;
+  return (size_t)P.wtab_bytes + 16 + items * sizeof(int4);
 }
 
 // Strip / row-buffer plan shared by both variants (exact, from the host mirrors of the tables).
@@ -200,6 +328,14 @@ inline int plan_stream(SParams& P, const AxisTables* th, const AxisTables* tw, i
       fmax = std::max<int>(fmax, (int)(o - lo + 1));
     }
   }
+  int shift = 0;
+  for (int64_t a = 0; a < oW; a += strip_ox)
+    for (int64_t o = a; o + 1 < std::min<int64_t>(oW, a + strip_ox); o += 2)
+      shift = std::max<int>(shift, tw->h_xmin[o + 1] - tw->h_xmin[o]);
+  P.kp = P.Kw + shift;
+  P.pairs = (int64_t)strip_ox * Ci >= 256 ? 1 : 0;  // enough independent items per row group to halve them
+  P.wtab_bytes = P.pairs ? (int)((size_t)((strip_ox + 1) / 2) * P.kp * sizeof(float2)) : (int)((size_t)strip_ox * P.Kw * sizeof(float));
+  if (P.kp >= (1 << 16) || (int64_t)((strip_ox + 1) / 2) * P.kp >= (1ll << 30)) return fail(AA_ERR_UNSUPPORTED, "stream: window too long");
   P.tg = tg;
   P.vr = (P.tg - 1 + fmax + 3) / 4 * 4;
   if (P.vr > 32) return fail(AA_ERR_UNSUPPORTED, "stream: too many output rows finish per input batch (upsampling in H)");
@@ -220,7 +356,7 @@ struct PlanKey {
   }
 };
 struct Plan {
-  int n_strips, strip_ox, vw, vr, tg, aln, in_pitch;
+  int n_strips, strip_ox, vw, vr, tg, aln, in_pitch, kp, pairs, wtab_bytes;
   size_t smem;
   int max_grid;  // SMs * resident CTAs per SM
 };
@@ -230,10 +366,13 @@ void plan_clear();
 inline void plan_apply(SParams& P, const Plan& pl) {
   P.n_strips = pl.n_strips; P.strip_ox = pl.strip_ox; P.vw = pl.vw; P.vr = pl.vr; P.tg = pl.tg; P.aln = pl.aln;
   P.in_pitch = pl.in_pitch;
+  P.kp = pl.kp;
+  P.pairs = pl.pairs;
+  P.wtab_bytes = pl.wtab_bytes;
   P.total_units = P.lin.planes * pl.n_strips * P.oH;
 }
 inline Plan plan_from(const SParams& P, size_t smem, int max_grid) {
-  return Plan{P.n_strips, P.strip_ox, P.vw, P.vr, P.tg, P.aln, P.in_pitch, smem, max_grid};
+  return Plan{P.n_strips, P.strip_ox, P.vw, P.vr, P.tg, P.aln, P.in_pitch, P.kp, P.pairs, P.wtab_bytes, smem, max_grid};
 }
 
 }  // namespace stream_detail

@@ -49,7 +49,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory"); }
 
-// staged-row reads
+// staged-row reads (raw registers; expand() converts uint8 just before the FMAs)
 template <typename in_t, int VEC> struct SLoad;
 template <> struct SLoad<float, 4> {
   static __device__ __forceinline__ void ld(const unsigned char* p, float (&v)[4]) {
@@ -58,9 +58,9 @@ template <> struct SLoad<float, 4> {
   }
 };
 template <> struct SLoad<uint8_t, 8> {
-  static __device__ __forceinline__ void ld(const unsigned char* p, float (&v)[8]) {
+  static __device__ __forceinline__ void ld(const unsigned char* p, uint32_t (&r)[2]) {
     const uint2 q = *reinterpret_cast<const uint2*>(p);
-    unpack4(q.x, v); unpack4(q.y, v + 4);
+    r[0] = q.x; r[1] = q.y;
   }
 };
 
@@ -71,15 +71,15 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
   constexpr int RPT = 4;
   constexpr int VW = NTC * VEC;  // row pitch of Vs in floats (== P.vw)
   constexpr int RS4 = (A + 1 + 3) / 4;
+  using RawT = typename Raw<in_t, VEC>::T;
+  constexpr int RN = Raw<in_t, VEC>::N;
   constexpr int ES = (int)sizeof(in_t);
   // layout: [stages][R][in_pitch] staged input | Vs[vr][vw] | Ws[strip_ox][Kw] | sxmin | sxsize | mbarriers
   unsigned char* stage_base = smem_raw;
   float* Vs = reinterpret_cast<float*>(stage_base + (size_t)STAGES * R * P.in_pitch);
-  float* Ws = Vs + (size_t)P.vr * P.vw;
-  int* sxmin = reinterpret_cast<int*>(Ws + (size_t)P.strip_ox * P.Kw);
-  int* sxsize = sxmin + P.strip_ox;
-  int2* colinfo = reinterpret_cast<int2*>(sxsize + ((P.strip_ox + 1) & ~1));  // [strip_ox * Ci]
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(colinfo + (size_t)P.strip_ox * P.Ci) + 7) & ~(uintptr_t)7);
+  float2* Wp = reinterpret_cast<float2*>(Vs + (size_t)P.vr * P.vw);                   // [pairs][kp]
+  int4* pinfo = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(Wp) + P.wtab_bytes + 15) & ~(uintptr_t)15);  // [pairs * Ci]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pinfo + (P.pairs ? (size_t)((P.strip_ox + 1) / 2) : (size_t)P.strip_ox) * P.Ci);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
 
   const int t = threadIdx.x;
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
 
   // =============================== consumers ========================================================
   constexpr int vw = VW;
-  int cur_strip = -1, strip_fl0 = 0, strip_nof = 0;
+  int cur_strip = -1, strip_fl0 = 0, strip_npc = 0;
   HRole role = {0, 1, 0, 1};
   for (int64_t u = u_begin; u < u_end;) {
     const int64_t col = u / oH;
@@ -146,25 +146,18 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
     const int ox1 = min((int)P.oW, ox0 + P.strip_ox);
     if (s != cur_strip) {
       consumer_sync();
-      const int nox = ox1 - ox0;
-      for (int i = t; i < nox * P.Kw; i += NTC) Ws[i] = __ldg(P.w_w + (int64_t)ox0 * P.Kw + i);
-      for (int i = t; i < nox; i += NTC) { sxmin[i] = __ldg(P.xmin_w + ox0 + i); sxsize[i] = __ldg(P.xsize_w + ox0 + i); }
+      strip_setup(P, t, NTC, ox0, ox1, Wp, pinfo, &strip_fl0, &strip_npc);
+      role = hphase_role(t, NTC, strip_npc);
       cur_strip = s;
       consumer_sync();
-      strip_fl0 = (sxmin[0] * Ci) & ~(P.aln - 1);
-      strip_nof = nox * Ci;
-      hphase_build_colinfo(colinfo, sxmin, sxsize, t, NTC, strip_nof, Ci, P.Kw, strip_fl0);
-      role = hphase_role(t, NTC, strip_nof);
-      consumer_sync();
     }
-    const int fl0 = strip_fl0;                                                // first flat element of the strip
-    const int fl_end = (sxmin[ox1 - ox0 - 1] + sxsize[ox1 - ox0 - 1]) * Ci;  // one past the last
+    const int fl0 = strip_fl0;                                                              // first flat element of the strip
+    const int fl_end = (__ldg(P.xmin_w + ox1 - 1) + __ldg(P.xsize_w + ox1 - 1)) * Ci;       // one past the last
     const bool valid = fl0 + VEC * t < fl_end;
     const int64_t yA = __ldg(P.xmin_h + oyA);
     const int64_t yB = (int64_t)__ldg(P.xmin_h + oyB - 1) + __ldg(P.xsize_h + oyB - 1);
     const float4* rp = reinterpret_cast<const float4*>(P.slot_h) + yA * RS4;
     float* op = P.out + (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p + (int64_t)ox0 * Ci;
-    const int nof = strip_nof;
     float* vdst = Vs + VEC * t;
     const unsigned char* my_in = stage_base + (size_t)VEC * ES * t;  // + stage*R*in_pitch + i*in_pitch
 
@@ -176,12 +169,11 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
     int gbase = oyA;
     int cnt = 0;
 
-    auto row = [&](const float (&v)[VEC], const float4 (&rq)[RS4]) {
+    auto row = [&](const RawT (&raw)[RN], const float4 (&rq)[RS4]) {
       const float* rw = reinterpret_cast<const float*>(rq);
-#pragma unroll
-      for (int a = 0; a < A; a++)
-#pragma unroll
-        for (int e = 0; e < VEC; e++) acc[a][e] = fmaf(rw[a], v[e], acc[a][e]);
+      float v[VEC];
+      expand<VEC>(raw, v);
+      vfma<A, VEC>(acc, v, rw);
       const int packed = __float_as_int(rw[A]);
       if (packed >> 24) {
         const int nfl = packed >> 24;
@@ -203,7 +195,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
     };
     auto hphase = [&]() {
       consumer_sync();
-      hphase_run<RPT, VW>(Vs, Ws, colinfo, op, P.lout.stride_h, Ci, nof, role, gbase, cnt);
+      hphase_run<RPT, VW>(P, Vs, Wp, pinfo, op, strip_npc, role, gbase, cnt);
       consumer_sync();
       gbase += cnt;
       cnt = 0;
@@ -214,7 +206,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
       const unsigned char* sp = my_in + (size_t)stage * R * P.in_pitch;
       mbar_wait(full0 + 8 * stage, phase);
       if (n == R) {
-        float v[R][VEC];
+        RawT v[R][RN];
         float4 rq[R][RS4];
 #pragma unroll
         for (int i = 0; i < R; i++) SLoad<in_t, VEC>::ld(sp + i * P.in_pitch, v[i]);
@@ -228,7 +220,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
         for (int i = 0; i < R; i++) row(v[i], rq[i]);
       } else {
         for (int i = 0; i < n; i++) {
-          float v[VEC];
+          RawT v[RN];
           float4 rq[RS4];
           SLoad<in_t, VEC>::ld(sp + i * P.in_pitch, v);
 #pragma unroll
@@ -258,8 +250,7 @@ int launch_tma_cfg(SParams& P, const AxisTables* th, const AxisTables* tw, int d
     int rc = plan_stream(P, th, tw, NTC * VEC, 16 / ES, VEC, R, 4);
     if (rc != AA_OK) return rc;
     P.in_pitch = (P.vw * ES + 15) & ~15;
-    const size_t smem_ = (size_t)STAGES * R * P.in_pitch + sizeof(float) * ((size_t)P.vr * P.vw + (size_t)P.strip_ox * P.Kw) +
-                         sizeof(int) * 2 * (size_t)(P.strip_ox + 1) * (1 + P.Ci) + 8 + 16 * STAGES;
+    const size_t smem_ = (size_t)STAGES * R * P.in_pitch + sizeof(float) * (size_t)P.vr * P.vw + strip_table_bytes(P) + 8 + 16 * STAGES;
     if (smem_ > 200 * 1024) return fail(AA_ERR_UNSUPPORTED, "stream/tma: shared memory plan too large");
     AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int occ = 0, sms = 0;
