@@ -57,7 +57,7 @@ typedef enum aa_dtype {
 #define AA_FLAG_FORCE_STREAM 2u  /* streaming fused kernel (fails with AA_ERR_UNSUPPORTED if the
                                     shape/layout is not eligible)                                   */
 #define AA_FLAG_STREAM_TMA 4u    /* streaming kernel: stage input rows with cp.async.bulk (TMA)     */
-#define AA_FLAG_STREAM_LDG 8u    /* streaming kernel: plain vectorised global loads                 */
+#define AA_FLAG_STREAM_LDG 8u    /* streaming kernel: plain vectorised global loads, single role    */
 
 /* A 4-D tensor view [n, c, h, w] with ELEMENT strides, resident on CUDA device `device`.
  * Supported layouts: channels_first (stride_w == 1) and channels_last (stride_c == 1,

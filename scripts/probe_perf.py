@@ -114,3 +114,4 @@ if "tma" in which:
     torch.cuda.synchronize()
     print("TMA vs LDG max abs diff (u8 cubic)", (y - ref).abs().max().item())
     del x
+
