@@ -27,7 +27,6 @@ constexpr int TXV = 64;         // float4 columns per tile
 constexpr int TXF = TXV * 4;    // flat output columns per tile (= threads: one column each in stage 1)
 constexpr int NTY = 4;          // thread rows in stages 0 and 2
 constexpr int NT = TXV * NTY;   // 256 threads
-constexpr int TY = 32;          // output rows per tile
 
 struct TParams {
   const void* in;
@@ -46,7 +45,7 @@ struct TParams {
 
 template <typename in_t> __device__ __forceinline__ float ldf(const in_t* p) { return (float)__ldg(p); }
 
-template <int KH, int KW, typename in_t>
+template <int KH, int KW, int TY, typename in_t>
 __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
   constexpr int HR = (KH + 1 + 3) / 4;  // float4 per row record {w[KH], first T row}
   extern __shared__ __align__(16) float smem[];
@@ -169,6 +168,7 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
     float* dst = op + (int64_t)(oy0 + ty) * P.lout.stride_h + ofv;
     const int64_t dstep = (int64_t)NTY * P.lout.stride_h;
     const bool full = P.vec_store && (ofv + 4 <= of1);
+#pragma unroll 2
     for (int oyl = ty; oyl < oy1 - oy0; oyl += NTY, dst += dstep) {
       float rec[HR * 4];
 #pragma unroll
@@ -195,37 +195,56 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
   }
 }
 
-template <int KH, int KW, typename in_t>
-int launch_k(TParams& P, int64_t nblocks, int nr_max, int nc_max, cudaStream_t stream) {
+template <int KH, int KW, int TY, typename in_t>
+int launch_ty(TParams& P, int64_t planes, const BandedAxis& ah, size_t smem_limit, cudaStream_t stream) {
   constexpr int HR = (KH + 1 + 3) / 4;
-  P.pr = nr_max + KH - 1;
-  int pcp = nc_max + (KW - 1) * P.Ci;
-  pcp |= 1;  // odd pitch
-  P.pcp = pcp;
+  // exact row plan for this tile height from the host mirror
+  int64_t nr = 1;
+  for (int64_t y0 = 0; y0 < P.out_h; y0 += TY) {
+    const int64_t y1 = std::min<int64_t>(P.out_h, y0 + TY) - 1;
+    nr = std::max<int64_t>(nr, (int64_t)ah.h_start[y1] + ah.h_size[y1] - ah.h_start[y0]);
+  }
+  if (nr > 1024) return fail(AA_ERR_UNSUPPORTED, "tile: input patch too large; use the streaming/general path");
+  P.pr = (int)nr + KH - 1;
+  P.tiles_y = (P.out_h + TY - 1) / TY;
   const size_t smem = sizeof(float) * ((size_t)P.pr * TXF + (size_t)TY * HR * 4 + (size_t)P.pr * P.pcp);
-  if (smem > 100 * 1024) return fail(AA_ERR_UNSUPPORTED, "tile: input patch too large; use the streaming/general path");
-  auto kern = aa_tile_kernel<KH, KW, in_t>;
+  if (smem > smem_limit) return fail(AA_ERR_UNSUPPORTED, "tile: input patch too large; use the streaming/general path");
+  const int64_t nblocks = (int64_t)P.tiles_x * P.tiles_y * planes;
+  if (nblocks <= 0) return AA_OK;
+  if (nblocks >= (1ll << 31)) return fail(AA_ERR_UNSUPPORTED, "tile: too many tiles");
+  auto kern = aa_tile_kernel<KH, KW, TY, in_t>;
   if (smem > 48 * 1024) AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)nblocks, NT, smem, stream>>>(P);
   AA_LAUNCH_CHECK("aa_tile_kernel");
   return AA_OK;
 }
 
+template <int KH, int KW, typename in_t>
+int launch_k(TParams& P, int64_t planes, const BandedAxis& ah, int nc_max, cudaStream_t stream) {
+  int pcp = nc_max + (KW - 1) * P.Ci;
+  pcp |= 1;  // odd pitch
+  P.pcp = pcp;
+  // tall tiles amortise the per-CTA setup when the patch stays small (upsampling-like gathers)
+  int rc = launch_ty<KH, KW, 64, in_t>(P, planes, ah, 40 * 1024, stream);
+  if (rc != AA_ERR_UNSUPPORTED) return rc;
+  return launch_ty<KH, KW, 32, in_t>(P, planes, ah, 100 * 1024, stream);
+}
+
 template <int KH, typename in_t>
-int launch_kh(TParams& P, int kw, int64_t nb, int nr, int nc, cudaStream_t s) {
-  if (kw <= 2) return launch_k<KH, 2, in_t>(P, nb, nr, nc, s);
-  if (kw <= 3) return launch_k<KH, 3, in_t>(P, nb, nr, nc, s);
-  if (kw <= 5) return launch_k<KH, 5, in_t>(P, nb, nr, nc, s);
-  if (kw <= 7) return launch_k<KH, 7, in_t>(P, nb, nr, nc, s);
+int launch_kh(TParams& P, int kw, int64_t nb, const BandedAxis& ah, int nc, cudaStream_t s) {
+  if (kw <= 2) return launch_k<KH, 2, in_t>(P, nb, ah, nc, s);
+  if (kw <= 3) return launch_k<KH, 3, in_t>(P, nb, ah, nc, s);
+  if (kw <= 5) return launch_k<KH, 5, in_t>(P, nb, ah, nc, s);
+  if (kw <= 7) return launch_k<KH, 7, in_t>(P, nb, ah, nc, s);
   return fail(AA_ERR_UNSUPPORTED, "tile: more than 7 horizontal taps");
 }
 
 template <typename in_t>
-int launch_in(TParams& P, int kh, int kw, int64_t nb, int nr, int nc, cudaStream_t s) {
-  if (kh <= 2) return launch_kh<2, in_t>(P, kw, nb, nr, nc, s);
-  if (kh <= 3) return launch_kh<3, in_t>(P, kw, nb, nr, nc, s);
-  if (kh <= 5) return launch_kh<5, in_t>(P, kw, nb, nr, nc, s);
-  if (kh <= 7) return launch_kh<7, in_t>(P, kw, nb, nr, nc, s);
+int launch_in(TParams& P, int kh, int kw, int64_t nb, const BandedAxis& ah, int nc, cudaStream_t s) {
+  if (kh <= 2) return launch_kh<2, in_t>(P, kw, nb, ah, nc, s);
+  if (kh <= 3) return launch_kh<3, in_t>(P, kw, nb, ah, nc, s);
+  if (kh <= 5) return launch_kh<5, in_t>(P, kw, nb, ah, nc, s);
+  if (kh <= 7) return launch_kh<7, in_t>(P, kw, nb, ah, nc, s);
   return fail(AA_ERR_UNSUPPORTED, "tile: more than 7 vertical taps");
 }
 
@@ -243,26 +262,18 @@ int launch_tile(const void* in, int in_dtype, const Layout& lin, void* out, cons
   P.w_start = aw.start; P.w_size = aw.size; P.w_w = (const float*)aw.w; P.w_pitch = aw.pitch;
   P.in_h = (int)ah.n_in; P.in_wf = (int)(aw.n_in * Ci); P.out_h = (int)ah.n_out; P.out_wf = (int)(aw.n_out * Ci);
   P.tiles_x = (P.out_wf + TXF - 1) / TXF;
-  P.tiles_y = (P.out_h + TY - 1) / TY;
-  // exact patch plan from the host mirrors of the tables
-  int64_t nr = 1, nc = 1;
-  for (int64_t y0 = 0; y0 < P.out_h; y0 += TY) {
-    const int64_t y1 = std::min<int64_t>(P.out_h, y0 + TY) - 1;
-    nr = std::max<int64_t>(nr, (int64_t)ah.h_start[y1] + ah.h_size[y1] - ah.h_start[y0]);
-  }
+  // exact column plan from the host mirror of the table (the row plan depends on the tile height)
+  int64_t nc = 1;
   for (int64_t f0 = 0; f0 < P.out_wf; f0 += TXF) {
     const int64_t f1 = std::min<int64_t>(P.out_wf, f0 + TXF) - 1;
     const int64_t x0 = f0 / Ci, x1 = f1 / Ci;
     nc = std::max<int64_t>(nc, ((int64_t)aw.h_start[x1] + aw.h_size[x1] - aw.h_start[x0]) * Ci);
   }
-  if (nr > 512 || nc > 4096) return fail(AA_ERR_UNSUPPORTED, "tile: input patch too large; use the streaming/general path");
+  if (nc > 4096) return fail(AA_ERR_UNSUPPORTED, "tile: input patch too large; use the streaming/general path");
   P.vec_store = (((uintptr_t)out) % 16 == 0) && (lout.stride_h % 4 == 0) && (lout.stride_n % 4 == 0) &&
                 (lout.Cp == 1 || lout.stride_p % 4 == 0);
-  const int64_t nblocks = (int64_t)P.tiles_x * P.tiles_y * lin.planes;
-  if (nblocks <= 0) return AA_OK;
-  if (nblocks >= (1ll << 31)) return fail(AA_ERR_UNSUPPORTED, "tile: too many tiles");
-  if (in_dtype == AA_F32) return launch_in<float>(P, kh_max, kw_max, nblocks, (int)nr, (int)nc, stream);
-  return launch_in<uint8_t>(P, kh_max, kw_max, nblocks, (int)nr, (int)nc, stream);
+  if (in_dtype == AA_F32) return launch_in<float>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream);
+  return launch_in<uint8_t>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream);
 }
 
 }  // namespace aa
