@@ -227,7 +227,9 @@ int launch_k(TParams& P, int64_t planes, const BandedAxis& ah, int nc_max, cudaS
   // tall tiles amortise the per-CTA setup when the patch stays small (upsampling-like gathers)
   int rc = launch_ty<KH, KW, 64, in_t>(P, planes, ah, 40 * 1024, stream);
   if (rc != AA_ERR_UNSUPPORTED) return rc;
-  return launch_ty<KH, KW, 32, in_t>(P, planes, ah, 100 * 1024, stream);
+  rc = launch_ty<KH, KW, 32, in_t>(P, planes, ah, 72 * 1024, stream);
+  if (rc != AA_ERR_UNSUPPORTED) return rc;
+  return launch_ty<KH, KW, 16, in_t>(P, planes, ah, 72 * 1024, stream);
 }
 
 template <int KH, typename in_t>

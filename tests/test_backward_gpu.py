@@ -98,3 +98,33 @@ def test_extension_matches_reference_api(cuda, golden):
     # uint8 in -> float32 out (fused cast)
     yu = m.linear_forward(x.byte(), (11, 17), False)
     assert yu.dtype == torch.float32
+
+
+def test_backward_no_out_of_bounds_access(cuda):
+    from interpolate_antialiasing_b200 import capi
+    import ctypes
+    g = torch.Generator().manual_seed(6)
+    for shape, osize in [((2, 3, 64, 96), (16, 24)), ((1, 4, 31, 45), (96, 128)), ((2, 1, 57, 64), (19, 20)), ((3, 3, 128, 128), (32, 32))]:
+        for cl in (False, True):
+            for mode in ("linear", "cubic"):
+                pad = 4096
+                gshape = (shape[0], shape[1]) + osize
+                n_in = int(np.prod(gshape)); n_out = int(np.prod(shape))
+                gb = torch.full((n_in + 2 * pad,), float("nan"), device=cuda)
+                ob = torch.full((n_out + 2 * pad,), -12345.0, device=cuda)
+                if cl:
+                    go = gb[pad:pad + n_in].view(gshape[0], gshape[2], gshape[3], gshape[1]).permute(0, 3, 1, 2)
+                    gi = ob[pad:pad + n_out].view(shape[0], shape[2], shape[3], shape[1]).permute(0, 3, 1, 2)
+                else:
+                    go = gb[pad:pad + n_in].view(gshape)
+                    gi = ob[pad:pad + n_out].view(shape)
+                src = torch.rand(gshape, generator=g)
+                go.copy_(src)
+                dg, di = capi.desc(go), capi.desc(gi)
+                capi.check(capi.lib().aa_resize_backward(ctypes.byref(dg), ctypes.byref(di), capi.FILTERS[mode], 0, 0,
+                                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                torch.cuda.synchronize()
+                assert torch.isfinite(gi).all(), (shape, osize, cl, mode)
+                assert (ob[:pad] == -12345.0).all() and (ob[pad + n_out:] == -12345.0).all()
+                want = O.backward_adjoint(src.numpy(), shape, mode, False)
+                np.testing.assert_allclose(gi.cpu().numpy(), want, rtol=1e-5, atol=1e-4)

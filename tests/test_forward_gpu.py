@@ -198,3 +198,44 @@ def test_edge_cases(cuda):
         capi.resize_forward(torch.rand((1, 3, 8, 8), device=cuda), (4, 4), 7)
     with pytest.raises(capi.AAError):  # non-NCHW/NHWC strides
         capi.resize_forward(torch.rand((1, 3, 8, 16), device=cuda)[:, :, :, ::2], (4, 4), "linear")
+
+
+def _guarded(shape, dtype, device, channels_last, pad=4096, fill=float("nan")):
+    """A tensor of `shape` carved out of a larger buffer whose margins hold canaries."""
+    n = int(np.prod(shape))
+    buf = torch.full((n + 2 * pad,), fill if dtype.is_floating_point else 255, dtype=dtype, device=device)
+    core = buf[pad:pad + n]
+    N, C, H, W = shape
+    t = core.view(N, H, W, C).permute(0, 3, 1, 2) if channels_last else core.view(N, C, H, W)
+    return buf, t, pad, n
+
+
+@pytest.mark.parametrize("flags_name", ["FLAG_AUTO", "FLAG_FORCE_STREAM", "FLAG_FORCE_GENERAL", "TMA"])
+def test_no_out_of_bounds_access(cuda, flags_name):
+    """compute-sanitizer is closed on this pool, so out-of-bounds traffic is caught with canaries: NaN
+    margins around the input poison the output if any kernel reads outside the tensor (even with a zero
+    weight), and the output's margins must stay untouched."""
+    from interpolate_antialiasing_b200 import capi
+    flags = (capi.FLAG_FORCE_STREAM | capi.FLAG_STREAM_TMA) if flags_name == "TMA" else getattr(capi, flags_name)
+    g = torch.Generator().manual_seed(5)
+    cases = [((2, 3, 64, 96), (16, 24)), ((1, 4, 96, 128), (31, 45)), ((2, 1, 57, 64), (19, 20)), ((1, 3, 40, 48), (80, 96)),
+             ((1, 3, 33, 64), (33, 64)), ((1, 2, 120, 36), (30, 72)), ((3, 3, 128, 128), (32, 32))]
+    for shape, osize in cases:
+        for cl in (False, True):
+            for mode in ("linear", "cubic"):
+                for dt in (torch.float32, torch.uint8):
+                    xb, x, _, _ = _guarded(shape, dt, cuda, cl)
+                    src = torch.rand(shape, generator=g) * 255
+                    x.copy_(src.to(dt))
+                    ob, out, pad, n = _guarded((shape[0], shape[1]) + osize, torch.float32, cuda, cl, fill=-12345.0)
+                    try:
+                        capi.resize_forward(x, osize, mode, False, flags, out=out)
+                    except capi.AAError as e:
+                        if "-2" in str(e) and flags != capi.FLAG_AUTO:
+                            continue
+                        raise
+                    torch.cuda.synchronize()
+                    assert torch.isfinite(out).all(), (shape, osize, cl, mode, dt, "read outside the input")
+                    assert (ob[:pad] == -12345.0).all() and (ob[pad + n:] == -12345.0).all(), "wrote outside the output"
+                    want = O.forward(src.to(dt).float().numpy(), osize, mode, False)
+                    _close(out.cpu().numpy(), want)
