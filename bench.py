@@ -87,7 +87,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -119,6 +119,26 @@ class ClockSampler:
                 continue
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Pin this process to the CPU cores local to its GPU (sysfs local_cpulist) so that the pinned host
+    buffers of the e2e leg are first-touched on the GPU's NUMA node.  Best effort; returns a note."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        txt = open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"cpus {txt} (GPU {bus} local)"
+    except Exception as e:  # noqa: BLE001
+        return f"unbound ({type(e).__name__})"
+    return "unbound"
 
 
 def make_inputs(cfg, dev, torch, n_images=None):
@@ -295,6 +315,7 @@ def main():
     # ---- e2e: host buffers through the C ABI, copies inside the timed region
     e2e = None
     if not args.no_e2e and cfg["kind"] == "forward":
+        numa_note = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else "single process, unbound"
         if cfg["cl"]:
             xh = torch.empty((cfg["N"], cfg["H"], cfg["W"], cfg["C"]), dtype=x.dtype, pin_memory=True).permute(0, 3, 1, 2)
             oh = torch.empty((cfg["N"], cfg["oH"], cfg["oW"], cfg["C"]), dtype=out.dtype, pin_memory=True).permute(0, 3, 1, 2)
@@ -318,7 +339,8 @@ def main():
         ok = bool(torch.allclose(oh.to(dev), out, rtol=1e-5, atol=1e-3))
         e2e = {"value": world * mpix(cfg) / dt, "unit": "Mpix/s", "h2d_bytes_per_step": xh.numel() * xh.element_size(),
                "d2h_bytes_per_step": oh.numel() * oh.element_size(), "ms_per_step": dt * 1e3, "steps": e2e_steps,
-               "api": "aa_resize_forward_host (C ABI, pinned host buffers)", "matches_device_result": ok}
+               "api": "aa_resize_forward_host (C ABI, pinned host buffers)", "matches_device_result": ok,
+               "host_affinity": numa_note}
         del xh, oh
 
     if rank == 0:

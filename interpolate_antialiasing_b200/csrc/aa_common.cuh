@@ -67,7 +67,6 @@ struct AxisTables {
   float* slot = nullptr;     // [in][RS]: A weights by slot (o % A), then (first_flush_o | nflush<<24)
   // host mirrors of the integer tables (for launch planning)
   std::vector<int32_t> h_xmin, h_xsize, h_omin, h_osize;
-  cudaEvent_t ready = nullptr;  // recorded on the building stream
   ~AxisTables();
 };
 

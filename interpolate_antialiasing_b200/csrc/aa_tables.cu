@@ -251,7 +251,6 @@ AxisTables::~AxisTables() {
     cudaSetDevice(device);
     if (block) cudaFree(block);
     if (slot) cudaFree(slot);
-    if (ready) cudaEventDestroy(ready);
     cudaSetDevice(cur);
   }
 }
@@ -337,8 +336,6 @@ int build_tables(AxisTables* t, cudaStream_t stream) {
     return fail(AA_ERR_INVALID, "internal: adjoint pitch bound too small (kt_max " + std::to_string(h.kt_max) +
                                     " > KT " + std::to_string(t->KT) + ")");
   if (!h.monotone) return fail(AA_ERR_INVALID, "internal: window tables are not monotone");
-  AA_CUDA_TRY(cudaEventCreateWithFlags(&t->ready, cudaEventDisableTiming));
-  AA_CUDA_TRY(cudaEventRecord(t->ready, stream));
   return AA_OK;
 }
 }  // namespace
@@ -352,9 +349,9 @@ int get_axis_tables(int device, int64_t in, int64_t out, int filter, int align, 
   std::lock_guard<std::mutex> lock(g_mu);
   auto it = g_cache.find(key);
   if (it != g_cache.end()) {
+    // a cached entry is complete (the builder synchronised its stream before publishing it), so a hit
+    // needs no stream dependency at all -- which also keeps hits legal under CUDA-graph capture
     *result = it->second;
-    // tables may have been built on another stream
-    AA_CUDA_TRY(cudaStreamWaitEvent(stream, it->second->ready, 0));
     return AA_OK;
   }
   auto t = std::make_shared<AxisTables>();
@@ -374,10 +371,7 @@ int get_axis_tables(int device, int64_t in, int64_t out, int filter, int align, 
 int ensure_slot_tables(AxisTables* t, int A, cudaStream_t stream) {
   std::lock_guard<std::mutex> lock(g_mu);
   if (t->dtype != AA_F32) return fail(AA_ERR_UNSUPPORTED, "slot tables are float only");
-  if (t->slot && t->slot_A == A) {
-    AA_CUDA_TRY(cudaStreamWaitEvent(stream, t->ready, 0));
-    return AA_OK;
-  }
+  if (t->slot && t->slot_A == A) return AA_OK;  // complete: the builder synchronised before publishing
   if (t->slot) return fail(AA_ERR_INVALID, "internal: slot tables requested with two different A");
   if (t->out >= (1 << 24)) return fail(AA_ERR_UNSUPPORTED, "streaming path needs out < 2^24");
   const int RS = (A + 1 + 3) / 4 * 4;
@@ -386,9 +380,9 @@ int ensure_slot_tables(AxisTables* t, int A, cudaStream_t stream) {
   aa_tables_slots<<<(unsigned)((t->in + NT - 1) / NT), NT, 0, stream>>>(
       t->in, A, RS, t->KT, t->xmin, t->xsize, t->omin, t->osize, (const float*)t->wT, t->slot);
   AA_LAUNCH_CHECK("aa_tables_slots");
+  AA_CUDA_TRY(cudaStreamSynchronize(stream));  // first use only
   t->slot_A = A;
   t->slot_RS = RS;
-  AA_CUDA_TRY(cudaEventRecord(t->ready, stream));
   return AA_OK;
 }
 

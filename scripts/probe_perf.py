@@ -115,3 +115,38 @@ if "tma" in which:
     print("TMA vs LDG max abs diff (u8 cubic)", (y - ref).abs().max().item())
     del x
 
+
+if "graph" in which:
+    # launch-latency-scale configs: stream-launched back to back vs CUDA-graph replay (device time per call)
+    def graph_time(fn, n=50):
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            fn()
+        s.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            for _ in range(n):
+                fn()
+        gr.replay(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); gr.replay(); b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+    def burst_time(fn, n=200):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+    x = torch.rand((1, 3, 438, 906), generator=g, device=dev) * 255
+    out = capi.resize_forward(x, (196, 320), "linear")
+    f1 = lambda: capi.resize_forward(x, (196, 320), "linear", False, capi.FLAG_AUTO, out=out)
+    b1 = 3 * (438 * 906 + 196 * 320) * 4
+    tg, tb = graph_time(f1), burst_time(f1)
+    print(f"cfg1 forward: graph replay {tg*1e3:7.2f} us/call ({b1/tg/1e6:7.1f} GB/s), python back-to-back {tb*1e3:7.2f} us/call")
+    go = torch.rand((64, 3, 128, 128), generator=g, device=dev)
+    f4 = lambda: capi.resize_backward(go, (64, 3, 512, 512), "linear")
+    b4 = 64 * 3 * (128 * 128 + 512 * 512) * 4
+    tb = burst_time(f4)
+    print(f"cfg4 backward: python back-to-back {tb*1e3:7.2f} us/call ({b4/tb/1e6:7.1f} GB/s, {b4/tb/1e6/PEAK*100:5.1f}% of peak)")

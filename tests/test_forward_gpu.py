@@ -239,3 +239,34 @@ def test_no_out_of_bounds_access(cuda, flags_name):
                     assert (ob[:pad] == -12345.0).all() and (ob[pad + n:] == -12345.0).all(), "wrote outside the output"
                     want = O.forward(src.to(dt).float().numpy(), osize, mode, False)
                     _close(out.cpu().numpy(), want)
+
+
+def test_cuda_graph_capture_and_replay(cuda):
+    """The C ABI is asynchronous and allocation-free once the table cache is warm (aa_warm_tables), so a
+    forward + backward pair can be captured in a CUDA graph and replayed (cfg1/cfg4 are
+    launch-latency-scale)."""
+    import ctypes
+    from interpolate_antialiasing_b200 import capi
+    g = torch.Generator().manual_seed(8)
+    x = (torch.rand((1, 3, 438, 906), generator=g) * 255).to(cuda)
+    go = torch.rand((1, 3, 196, 320), generator=g).to(cuda)
+    out = torch.empty((1, 3, 196, 320), device=cuda)
+    gin = torch.empty_like(x)
+    L = capi.lib()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        capi.check(L.aa_warm_tables(438, 906, 196, 320, capi.TRIANGLE, 0, capi.F32, 0, ctypes.c_void_p(s.cuda_stream)))
+        capi.resize_forward(x, (196, 320), "linear", out=out)      # warm-up outside capture
+    s.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s):
+        capi.resize_forward(x, (196, 320), "linear", out=out)
+        dg, di = capi.desc(go), capi.desc(gin)
+        capi.check(L.aa_resize_backward(ctypes.byref(dg), ctypes.byref(di), capi.TRIANGLE, 0, 0,
+                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    out.zero_(); gin.zero_()
+    x.mul_(0.5)                      # replay must see the new contents of the same buffers
+    graph.replay()
+    torch.cuda.synchronize()
+    _close(out.cpu().numpy(), O.forward(x.cpu().numpy(), (196, 320), "linear", False))
+    np.testing.assert_allclose(gin.cpu().numpy(), O.backward_adjoint(go.cpu().numpy(), x.shape, "linear", False), rtol=1e-5, atol=1e-4)
