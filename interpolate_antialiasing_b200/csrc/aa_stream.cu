@@ -25,6 +25,8 @@
 // separable sum with fp32 rounding of the intermediate; the difference is pure rounding
 // (measured <= 1.3e-4 abs / 2.3e-6 rel on a 0..255 scale against the reference, tolerance
 // 1e-3 abs / 1e-5 rel -- tests/test_forward_gpu.py).  The bit-exact order lives in aa_general.cu.
+#include <stdlib.h>
+
 #include <map>
 #include <mutex>
 
@@ -199,7 +201,12 @@ int launch_cfg(SParams& P, const AxisTables* th, const AxisTables* tw, int devic
   plan_apply(P, pl);
   const size_t smem = pl.smem;
   const int64_t min_units = 4;  // do not cut segments shorter than this many output rows
-  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(pl.max_grid, P.total_units / min_units));
+  // up to 2x more CTAs than fit at once: the hardware block scheduler then evens out SM-to-SM speed differences
+  // at the tail (measured +1 % on cfg2 in two same-box A/B runs; 3x was not reproducible; each extra cut costs one window's halo rows)
+  // but never cut work finer than about one column (oH output rows) per CTA
+  static const int gmul = [] { const char* e = getenv("AA_STREAM_GRID_MUL"); return e ? std::max(1, atoi(e)) : 2; }();  // tuning knob
+  const int64_t want = std::min<int64_t>((int64_t)pl.max_grid * gmul, std::max<int64_t>(pl.max_grid, P.total_units / P.oH));
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(want, P.total_units / min_units));
   kern<<<(unsigned)grid, C::NT, smem, stream>>>(P);
   AA_LAUNCH_CHECK("aa_stream_kernel");
   return AA_OK;
