@@ -58,6 +58,7 @@ typedef enum aa_dtype {
                                     shape/layout is not eligible)                                   */
 #define AA_FLAG_STREAM_TMA 4u    /* streaming kernel: stage input rows with cp.async.bulk (TMA)     */
 #define AA_FLAG_STREAM_LDG 8u    /* streaming kernel: plain vectorised global loads, single role    */
+#define AA_FLAG_ROUND_NEAREST 32u /* uint8 output: round to nearest (PIL) instead of truncating (.byte()) */
 
 /* A 4-D tensor view [n, c, h, w] with ELEMENT strides, resident on CUDA device `device`.
  * Supported layouts: channels_first (stride_w == 1) and channels_last (stride_c == 1,
@@ -114,7 +115,9 @@ int aa_clear_table_cache(void);
  * general path, as the reference; see DESIGN.md for the streaming path's order).
  * Replaces ti_upsample_{bilinear,bicubic,nearest}2d_cpu, aa_interpolation_impl.h:731-807, i.e.
  * the body of linear_forward / cubic_forward / nearest_forward, for already-allocated outputs.
- * in->dtype: AA_U8 | AA_F32 | AA_F64; out->dtype: AA_F32 (for u8/f32 inputs) or AA_F64 (f64).
+ * in->dtype: AA_U8 | AA_F32 | AA_F64; out->dtype: AA_F32 (for u8/f32 inputs) or AA_F64 (f64), or
+ * AA_U8 (u8/f32 inputs) for the fused epilogue: clamp to [0,255] then truncate like the reference's caller
+ * (torch.clamp + .byte(), test.py:71-75), or round to nearest with AA_FLAG_ROUND_NEAREST.
  * n, c must match; in and out must be in the same memory format.  n == 0 is a no-op. */
 int aa_resize_forward(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter,
                       int align_corners, uint32_t flags, void* cuda_stream);

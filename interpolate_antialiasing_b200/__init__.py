@@ -18,7 +18,7 @@ from . import capi
 from ._build_ext import EXT, EXT_NAME, LIB
 
 __all__ = ["load", "linear_forward", "cubic_forward", "nearest_forward", "linear_backward", "cubic_backward",
-           "nearest_backward", "linear_backward_nonaa", "forward_with_flags", "AAResize", "aa_resize", "capi"]
+           "nearest_backward", "linear_backward_nonaa", "forward_with_flags", "resize_to_uint8", "AAResize", "aa_resize", "capi"]
 
 _ext = None
 
@@ -70,6 +70,12 @@ def linear_backward_nonaa(grad_output, output_size, input_size, align_corners=Fa
 
 def forward_with_flags(input, output_size, align_corners, filter, flags):
     return load().forward_with_flags(input, list(output_size), align_corners, capi.FILTERS.get(filter, filter), flags)
+
+
+def resize_to_uint8(input, output_size, mode="bilinear", align_corners=False, round_nearest=True):
+    """uint8/float32 in -> uint8 out with the clamp + round epilogue fused into the kernel's store
+    (round_nearest=False reproduces the reference harness' clamp + `.byte()` truncation, test.py:71-75)."""
+    return load().forward_u8(input, list(output_size), align_corners, capi.FILTERS[mode], round_nearest)
 
 
 from .functional import AAResize, aa_resize  # noqa: E402

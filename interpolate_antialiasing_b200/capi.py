@@ -11,7 +11,7 @@ from ._build_ext import LIB
 
 BOX, TRIANGLE, CUBIC = 0, 1, 2
 U8, F32, F64 = 0, 1, 2
-FLAG_AUTO, FLAG_FORCE_GENERAL, FLAG_FORCE_STREAM, FLAG_STREAM_TMA, FLAG_STREAM_LDG = 0, 1, 2, 4, 8
+FLAG_AUTO, FLAG_FORCE_GENERAL, FLAG_FORCE_STREAM, FLAG_STREAM_TMA, FLAG_STREAM_LDG, FLAG_ROUND_NEAREST = 0, 1, 2, 4, 8, 32
 FILTERS = {"nearest": BOX, "box": BOX, "bilinear": TRIANGLE, "linear": TRIANGLE, "bicubic": CUBIC, "cubic": CUBIC}
 
 EXPORTS = [
@@ -115,14 +115,15 @@ def build_tables(in_size, out_size, filter, align_corners=False, dtype=None, dev
     return xmin, xsize, w
 
 
-def resize_forward(x, output_size, filter, align_corners=False, flags=FLAG_AUTO, out=None):
-    """C-ABI forward on a CUDA tensor already contiguous in channels_first or channels_last."""
+def resize_forward(x, output_size, filter, align_corners=False, flags=FLAG_AUTO, out=None, out_u8=False):
+    """C-ABI forward on a CUDA tensor already contiguous in channels_first or channels_last.
+    out_u8=True allocates a uint8 output: the clamp + truncate/round epilogue is fused (FLAG_ROUND_NEAREST)."""
     import torch
     N, C, H, W = x.shape
     oH, oW = int(output_size[0]), int(output_size[1])
     if out is None:
         cl = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
-        out = torch.empty((N, C, oH, oW), dtype=torch.float64 if x.dtype == torch.float64 else torch.float32,
+        out = torch.empty((N, C, oH, oW), dtype=torch.uint8 if out_u8 else (torch.float64 if x.dtype == torch.float64 else torch.float32),
                           device=x.device, memory_format=torch.channels_last if cl else torch.contiguous_format)
     di, do = desc(x), desc(out)
     check(lib().aa_resize_forward(ctypes.byref(di), ctypes.byref(do), _filter(filter), int(align_corners), flags, _stream(x)))

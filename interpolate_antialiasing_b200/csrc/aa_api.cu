@@ -91,7 +91,11 @@ int forward_impl(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter
   if (in->n != out->n || in->c != out->c) return fail(AA_ERR_INVALID, "input and output must agree in n and c");
   if (in->device != out->device) return fail(AA_ERR_INVALID, "input and output must live on the same device");
   const int tdtype = in->dtype == AA_F64 ? AA_F64 : AA_F32;
-  if (out->dtype != tdtype) return fail(AA_ERR_INVALID, "output dtype must be f32 for u8/f32 inputs and f64 for f64 inputs");
+  OutEpi epi;
+  epi.u8 = (out->dtype == AA_U8 && tdtype == AA_F32) ? 1 : 0;
+  epi.round = (flags & AA_FLAG_ROUND_NEAREST) ? 1 : 0;
+  if (out->dtype != tdtype && !epi.u8)
+    return fail(AA_ERR_INVALID, "output dtype must be f32 (or u8 with the fused clamp/round epilogue) for u8/f32 inputs and f64 for f64 inputs");
   if (in->n == 0) return AA_OK;  // empty batch is allowed (aa_interpolation_impl.h:747-750)
   Layout lin, lout;
   bool in_cl = false, out_cl = false;
@@ -113,18 +117,18 @@ int forward_impl(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter
     const bool few_taps = th->xsize_max <= 7 && tw->xsize_max <= 7;
     if (few_taps && !(flags & AA_FLAG_FORCE_STREAM)) {
       rc = launch_tile(in->data, in->dtype, lin, out->data, lout, fwd_axis(th.get()), fwd_axis(tw.get()), th->xsize_max,
-                       tw->xsize_max, stream);
+                       tw->xsize_max, epi, stream);
       if (rc != AA_ERR_UNSUPPORTED) return rc;
     }
     rc = launch_stream(in->data, in->dtype, lin, out->data, lout, th.get(), tw.get(), in->h, in->w, out->h, out->w,
-                       flags, stream);
+                       flags, epi, stream);
     if (rc == AA_OK) return rc;
     if (rc != AA_ERR_UNSUPPORTED || (flags & AA_FLAG_FORCE_STREAM)) return rc;
   } else if (flags & AA_FLAG_FORCE_STREAM) {
     return fail(AA_ERR_UNSUPPORTED, "stream path: f32/u8 only");
   }
   return launch_general(in->data, in->dtype, lin, out->data, out->dtype, lout, fwd_axis(th.get()), fwd_axis(tw.get()),
-                        /*exact=*/true, stream);
+                        /*exact=*/true, epi, stream);
 }
 
 int backward_check(const aa_tensor_desc* gout, const aa_tensor_desc* gin, Layout* lo, Layout* li) {
@@ -228,11 +232,11 @@ int aa_resize_backward(const aa_tensor_desc* gout, const aa_tensor_desc* gin, in
   if ((rc = get_axis_tables(gout->device, gin->w, gout->w, filter, align_corners, gout->dtype, stream, &tw)) != AA_OK) return rc;
   if (gout->dtype == AA_F32 && !(flags & AA_FLAG_FORCE_GENERAL)) {
     rc = launch_tile(gout->data, gout->dtype, lo, gin->data, li, adj_axis(th.get()), adj_axis(tw.get()), th->kt_max,
-                     tw->kt_max, stream);
+                     tw->kt_max, OutEpi(), stream);
     if (rc != AA_ERR_UNSUPPORTED) return rc;
   }
   return launch_general(gout->data, gout->dtype, lo, gin->data, gin->dtype, li, adj_axis(th.get()), adj_axis(tw.get()),
-                        /*exact=*/false, stream);
+                        /*exact=*/false, OutEpi(), stream);
 }
 
 int aa_resize_backward_nonaa_bilinear(const aa_tensor_desc* gout, const aa_tensor_desc* gin, int align_corners,
@@ -271,7 +275,7 @@ int aa_resize_forward_host(const aa_tensor_desc* in, const aa_tensor_desc* out, 
   const int dev = in->device;
   if (dev < 0 || dev >= 64) return fail(AA_ERR_INVALID, "bad device ordinal");
   const size_t ies = in->dtype == AA_U8 ? 1 : (in->dtype == AA_F32 ? 4 : 8);
-  const size_t oes = out->dtype == AA_F32 ? 4 : 8;
+  const size_t oes = out->dtype == AA_U8 ? 1 : (out->dtype == AA_F32 ? 4 : 8);
   const size_t img_in = (size_t)in->c * in->h * in->w, img_out = (size_t)out->c * out->h * out->w;
   if ((in->n > 1 && (size_t)in->stride_n != img_in) || (out->n > 1 && (size_t)out->stride_n != img_out))
     return fail(AA_ERR_UNSUPPORTED, "host path needs densely packed images (stride_n == c*h*w)");

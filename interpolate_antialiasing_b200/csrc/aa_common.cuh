@@ -93,6 +93,25 @@ struct Layout {
 // Classifies a tensor desc; returns AA_ERR_UNSUPPORTED for anything but dense-row NCHW/NHWC.
 int classify_layout(const aa_tensor_desc& t, bool prefer_channels_last, Layout* out, bool* is_channels_last);
 
+// ---- fused output epilogue --------------------------------------------------------------------
+// out dtype AA_U8: clamp to [0,255] then truncate (what the reference's caller does: torch.clamp +
+// .byte(), /root/reference/test.py:71-75) or, with AA_FLAG_ROUND_NEAREST, add 0.5 first (PIL's rounding).
+struct OutEpi {
+  int u8 = 0;     // 1: store uint8
+  int round = 0;  // 1: round to nearest instead of truncating
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned int aa_to_u8(float v, int round) {
+  v = fminf(fmaxf(v, 0.f), 255.f);
+  return (unsigned int)(round ? v + 0.5f : v);
+}
+// element store through a base pointer whose element type depends on the epilogue
+__device__ __forceinline__ void aa_store(void* base, int64_t idx, float v, const OutEpi e) {
+  if (e.u8) reinterpret_cast<uint8_t*>(base)[idx] = (uint8_t)aa_to_u8(v, e.round);
+  else reinterpret_cast<float*>(base)[idx] = v;
+}
+#endif
+
 // ---- kernels' host launchers ---------------------------------------------------------------
 struct BandedAxis {  // one axis of a banded separable apply: out index i reads in [start[i], start[i]+size[i])
   const int32_t* start;
@@ -108,19 +127,19 @@ struct BandedAxis {  // one axis of a banded separable apply: out index i reads 
 // exact=true: separate multiply and add (bit-identical to the reference's C++), else FMA.
 int launch_general(const void* in, int in_dtype, const Layout& lin, void* out, int out_dtype,
                    const Layout& lout, const BandedAxis& ah, const BandedAxis& aw, bool exact,
-                   cudaStream_t stream);
+                   OutEpi epi, cudaStream_t stream);
 
 // Tile kernel for gathers with few taps (backward of downsampling, forward upsampling): input patch
 // in shared memory -> horizontal pass -> shared memory -> vertical pass -> 128-bit stores.  f32 out,
 // f32/u8 in.  Returns AA_ERR_UNSUPPORTED when the patch would not fit so the caller can fall back.
 int launch_tile(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout,
-                const BandedAxis& ah, const BandedAxis& aw, int kh_max, int kw_max, cudaStream_t stream);
+                const BandedAxis& ah, const BandedAxis& aw, int kh_max, int kw_max, OutEpi epi, cudaStream_t stream);
 
 // Streaming fused kernel (downsampling in both axes, f32/u8 in, f32 out).  Returns
 // AA_ERR_UNSUPPORTED when not eligible so the caller can fall back to launch_general.
 int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout,
                   AxisTables* th, AxisTables* tw, int64_t H, int64_t W, int64_t oH, int64_t oW,
-                  uint32_t flags, cudaStream_t stream);
+                  uint32_t flags, OutEpi epi, cudaStream_t stream);
 
 int launch_backward_nonaa(const void* gout, void* gin, int dtype, const Layout& lout, const Layout& lin,
                           int64_t oH, int64_t oW, int64_t H, int64_t W, int align, cudaStream_t stream);

@@ -51,6 +51,7 @@ template <bool EXACT> __device__ __forceinline__ double mac(double acc, double a
 struct GParams {
   const void* in;
   void* out;
+  OutEpi epi;
   Layout lin, lout;
   const int32_t *h_start, *h_size, *w_start, *w_size;
   const void *h_w, *w_w;
@@ -137,7 +138,16 @@ __global__ void __launch_bounds__(TW* NTY) aa_general_kernel(const GParams P) {
 #pragma unroll
     for (int r = 0; r < RPT; r++) {
       const int64_t oy = oy0 + ty + r * NTY;
-      if (oy < P.out_h) op[oy * P.lout.stride_h + of] = acc[r];
+      if (oy < P.out_h) {
+        if constexpr (sizeof(acc_t) == 4) {
+          if (P.epi.u8) {
+            const int64_t off = (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p + oy * P.lout.stride_h + of;
+            reinterpret_cast<uint8_t*>(P.out)[off] = (uint8_t)aa_to_u8((float)acc[r], P.epi.round);
+            continue;
+          }
+        }
+        op[oy * P.lout.stride_h + of] = acc[r];
+      }
     }
   }
 }
@@ -239,9 +249,13 @@ __global__ void aa_nonaa_bilinear_backward(const T* __restrict__ gout, T* __rest
 
 int launch_general(const void* in, int in_dtype, const Layout& lin, void* out, int out_dtype,
                    const Layout& lout, const BandedAxis& ah, const BandedAxis& aw, bool exact,
-                   cudaStream_t stream) {
+                   OutEpi epi, cudaStream_t stream) {
   GParams P;
-  P.in = in; P.out = out; P.lin = lin; P.lout = lout;
+  P.in = in; P.out = out; P.epi = epi; P.lin = lin; P.lout = lout;
+  if (epi.u8) {
+    if (in_dtype == AA_F64) return fail(AA_ERR_UNSUPPORTED, "uint8 output needs u8 or f32 input");
+    out_dtype = AA_F32;  // accumulate in f32, convert at the store
+  }
   P.h_start = ah.start; P.h_size = ah.size; P.h_w = ah.w; P.h_pitch = ah.pitch;
   P.w_start = aw.start; P.w_size = aw.size; P.w_w = aw.w; P.w_pitch = aw.pitch;
   P.in_h = ah.n_in; P.in_w = aw.n_in; P.out_h = ah.n_out; P.out_w = aw.n_out;

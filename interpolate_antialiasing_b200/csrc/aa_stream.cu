@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
     const int64_t yB = (int64_t)__ldg(P.xmin_h + oyB - 1) + __ldg(P.xsize_h + oyB - 1);
     const in_t* ip = (const in_t*)P.in + (plane / P.lin.Cp) * P.lin.stride_n + (plane % P.lin.Cp) * P.lin.stride_p + fmy + yA * stride_h;
     const float4* rp = reinterpret_cast<const float4*>(P.slot_h) + yA * RS4;
-    float* op = P.out + (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p + (int64_t)ox0 * Ci;
+    const int64_t op = (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p + (int64_t)ox0 * Ci;  // element offset
     float* vdst = Vs + VEC * t;
 
     float acc[A][VEC];
@@ -249,7 +249,7 @@ void plan_clear() {
 
 int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout,
                   AxisTables* th, AxisTables* tw, int64_t H, int64_t W, int64_t oH, int64_t oW,
-                  uint32_t flags, cudaStream_t stream) {
+                  uint32_t flags, OutEpi epi, cudaStream_t stream) {
   if (in_dtype != AA_F32 && in_dtype != AA_U8) return fail(AA_ERR_UNSUPPORTED, "stream: input must be f32 or u8");
   if (th->dtype != AA_F32 || tw->dtype != AA_F32) return fail(AA_ERR_UNSUPPORTED, "stream: f32 tables only");
   if (th->kt_max > kMaxA) return fail(AA_ERR_UNSUPPORTED, "stream: too many output rows per input row (upsampling in H)");
@@ -271,7 +271,7 @@ int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, co
   if (rc != AA_OK) return rc;
 
   SParams P;
-  P.in = in; P.out = (float*)out; P.lin = lin; P.lout = lout; P.Ci = lin.Ci;
+  P.in = in; P.out = out; P.epi = epi; P.lin = lin; P.lout = lout; P.Ci = lin.Ci;
   P.H = H; P.oH = oH; P.oW = oW;
   P.slot_h = th->slot; P.RS = th->slot_RS;
   P.xmin_h = th->xmin; P.xsize_h = th->xsize;

@@ -12,7 +12,8 @@ constexpr int kMaxA = 6;
 
 struct SParams {
   const void* in;
-  float* out;
+  void* out;    // float* or uint8_t* (epi.u8)
+  OutEpi epi;
   Layout lin, lout;
   int Ci;
   int64_t H, oH, oW;
@@ -199,8 +200,9 @@ __device__ __forceinline__ void strip_setup(const SParams& P, int t, int nthread
 // zero padding and the data pointer stops advancing, so no element outside the true windows is touched.
 template <int RPT, int VW>
 __device__ __forceinline__ void hphase_run_pairs(const float* __restrict__ Vs, const float2* __restrict__ Wp,
-                                           const int4* __restrict__ pinfo, float* __restrict__ op, int64_t out_stride_h,
-                                           int Ci, int npc, const HRole role, int gbase, int cnt) {
+                                           const int4* __restrict__ pinfo, void* __restrict__ op, int64_t op_off,
+                                           const OutEpi epi, int64_t out_stride_h, int Ci, int npc, const HRole role, int gbase,
+                                           int cnt) {
   const int nrg = (cnt + RPT - 1) / RPT;
   for (int rg = role.rg0; rg < nrg; rg += role.rg_par) {
     for (int cfb = role.cf0 - (role.cf0 & 31); cfb < npc; cfb += role.cf_step) {
@@ -225,13 +227,13 @@ __device__ __forceinline__ void hphase_run_pairs(const float* __restrict__ Vs, c
         vp += (j + 1 < len) ? Ci : 0;
       }
       if (act) {
-        float* dst = op + (int64_t)(gbase + rg * RPT) * out_stride_h + pi.w;
+        const int64_t dst = op_off + (int64_t)(gbase + rg * RPT) * out_stride_h + pi.w;
         const bool hasb = (pi.z >> 16) != 0;
 #pragma unroll
         for (int r = 0; r < RPT; r++) {
           if (rg * RPT + r < cnt) {
-            dst[(int64_t)r * out_stride_h] = h[r].x;
-            if (hasb) dst[(int64_t)r * out_stride_h + Ci] = h[r].y;
+            aa_store(op, dst + (int64_t)r * out_stride_h, h[r].x, epi);
+            if (hasb) aa_store(op, dst + (int64_t)r * out_stride_h + Ci, h[r].y, epi);
           }
         }
       }
@@ -241,8 +243,9 @@ __device__ __forceinline__ void hphase_run_pairs(const float* __restrict__ Vs, c
 // single-column form (P.pairs == 0): one item = one flat output column x RPT rows, FFMA2 over row pairs
 template <int RPT, int VW>
 __device__ __forceinline__ void hphase_run_single(const float* __restrict__ Vs, const float* __restrict__ Ws,
-                                                  const int4* __restrict__ pinfo, float* __restrict__ op, int64_t out_stride_h,
-                                                  int Ci, int nof, const HRole role, int gbase, int cnt) {
+                                                  const int4* __restrict__ pinfo, void* __restrict__ op, int64_t op_off,
+                                                  const OutEpi epi, int64_t out_stride_h, int Ci, int nof, const HRole role,
+                                                  int gbase, int cnt) {
   const int nrg = (cnt + RPT - 1) / RPT;
   for (int rg = role.rg0; rg < nrg; rg += role.rg_par) {
     for (int cfb = role.cf0 - (role.cf0 & 31); cfb < nof; cfb += role.cf_step) {
@@ -269,19 +272,19 @@ __device__ __forceinline__ void hphase_run_single(const float* __restrict__ Vs, 
         vp += (j + 1 < xs) ? Ci : 0;
       }
       if (act) {
-        float* dst = op + (int64_t)(gbase + rg * RPT) * out_stride_h + cf;
+        const int64_t dst = op_off + (int64_t)(gbase + rg * RPT) * out_stride_h + cf;
 #pragma unroll
         for (int r = 0; r < RPT; r++)
-          if (rg * RPT + r < cnt) dst[(int64_t)r * out_stride_h] = h[r];
+          if (rg * RPT + r < cnt) aa_store(op, dst + (int64_t)r * out_stride_h, h[r], epi);
       }
     }
   }
 }
 template <int RPT, int VW>
-__device__ __forceinline__ void hphase_run(const SParams& P, const float* Vs, const float2* Wp, const int4* pinfo, float* op,
+__device__ __forceinline__ void hphase_run(const SParams& P, const float* Vs, const float2* Wp, const int4* pinfo, int64_t op_off,
                                            int npc, const HRole role, int gbase, int cnt) {
-  if (P.pairs) hphase_run_pairs<RPT, VW>(Vs, Wp, pinfo, op, P.lout.stride_h, P.Ci, npc, role, gbase, cnt);
-  else hphase_run_single<RPT, VW>(Vs, reinterpret_cast<const float*>(Wp), pinfo, op, P.lout.stride_h, P.Ci, npc, role, gbase, cnt);
+  if (P.pairs) hphase_run_pairs<RPT, VW>(Vs, Wp, pinfo, P.out, op_off, P.epi, P.lout.stride_h, P.Ci, npc, role, gbase, cnt);
+  else hphase_run_single<RPT, VW>(Vs, reinterpret_cast<const float*>(Wp), pinfo, P.out, op_off, P.epi, P.lout.stride_h, P.Ci, npc, role, gbase, cnt);
 }
 // bytes of the strip tables (after Vs) for a plan
 inline size_t strip_table_bytes(const SParams& P) {

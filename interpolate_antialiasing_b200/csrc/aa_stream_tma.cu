@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
     const int64_t yA = __ldg(P.xmin_h + oyA);
     const int64_t yB = (int64_t)__ldg(P.xmin_h + oyB - 1) + __ldg(P.xsize_h + oyB - 1);
     const float4* rp = reinterpret_cast<const float4*>(P.slot_h) + yA * RS4;
-    float* op = P.out + (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p + (int64_t)ox0 * Ci;
+    const int64_t op = (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p + (int64_t)ox0 * Ci;  // element offset
     float* vdst = Vs + VEC * t;
     const unsigned char* my_in = stage_base + (size_t)VEC * ES * t;  // + stage*R*in_pitch + i*in_pitch
 

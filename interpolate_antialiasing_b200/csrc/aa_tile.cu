@@ -30,7 +30,8 @@ constexpr int NT = TXV * NTY;   // 256 threads
 
 struct TParams {
   const void* in;
-  float* out;
+  void* out;  // float* or uint8_t* (epi.u8)
+  OutEpi epi;
   Layout lin, lout;
   int Ci;
   const int32_t *h_start, *h_size, *w_start, *w_size;
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
   const int64_t plane = b;
   const int Ci = P.Ci;
   const in_t* ip = (const in_t*)P.in + (plane / P.lin.Cp) * P.lin.stride_n + (plane % P.lin.Cp) * P.lin.stride_p;
-  float* op = P.out + (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p;
+  const int64_t op = (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p;  // element offset
 
   // tile extents (starts and ends are non-decreasing in the output index)
   const int oy0 = tile_y * TY, oy1 = min(P.out_h, oy0 + TY);
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
   // ---- stage 2: vertical pass + store
   const int ofv = of0 + 4 * tx;
   if (ofv < of1) {
-    float* dst = op + (int64_t)(oy0 + ty) * P.lout.stride_h + ofv;
+    int64_t dst = op + (int64_t)(oy0 + ty) * P.lout.stride_h + ofv;
     const int64_t dstep = (int64_t)NTY * P.lout.stride_h;
     const bool full = P.vec_store && (ofv + 4 <= of1);
 #pragma unroll 2
@@ -184,12 +185,18 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
         a.x = fmaf(v.x, rec[k], a.x); a.y = fmaf(v.y, rec[k], a.y); a.z = fmaf(v.z, rec[k], a.z); a.w = fmaf(v.w, rec[k], a.w);
       }
       if (full) {
-        *reinterpret_cast<float4*>(dst) = a;
+        if (P.epi.u8) {
+          const unsigned int pk = aa_to_u8(a.x, P.epi.round) | (aa_to_u8(a.y, P.epi.round) << 8) |
+                                  (aa_to_u8(a.z, P.epi.round) << 16) | (aa_to_u8(a.w, P.epi.round) << 24);
+          *reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(P.out) + dst) = pk;
+        } else {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + dst) = a;
+        }
       } else {
-        dst[0] = a.x;
-        if (ofv + 1 < of1) dst[1] = a.y;
-        if (ofv + 2 < of1) dst[2] = a.z;
-        if (ofv + 3 < of1) dst[3] = a.w;
+        aa_store(P.out, dst, a.x, P.epi);
+        if (ofv + 1 < of1) aa_store(P.out, dst + 1, a.y, P.epi);
+        if (ofv + 2 < of1) aa_store(P.out, dst + 2, a.z, P.epi);
+        if (ofv + 3 < of1) aa_store(P.out, dst + 3, a.w, P.epi);
       }
     }
   }
@@ -253,13 +260,13 @@ int launch_in(TParams& P, int kh, int kw, int64_t nb, const BandedAxis& ah, int 
 }  // namespace
 
 int launch_tile(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout,
-                const BandedAxis& ah, const BandedAxis& aw, int kh_max, int kw_max, cudaStream_t stream) {
+                const BandedAxis& ah, const BandedAxis& aw, int kh_max, int kw_max, OutEpi epi, cudaStream_t stream) {
   if (in_dtype != AA_F32 && in_dtype != AA_U8) return fail(AA_ERR_UNSUPPORTED, "tile: f32/u8 input only");
   if (kh_max > 7 || kw_max > 7) return fail(AA_ERR_UNSUPPORTED, "tile: more than 7 taps; use the streaming/general path");
   const int Ci = lin.Ci;
   if (aw.n_out * Ci >= (1ll << 30) || aw.n_in * Ci >= (1ll << 30) || ah.n_out >= (1ll << 30)) return fail(AA_ERR_UNSUPPORTED, "tile: size limits");
   TParams P;
-  P.in = in; P.out = (float*)out; P.lin = lin; P.lout = lout; P.Ci = Ci;
+  P.in = in; P.out = out; P.epi = epi; P.lin = lin; P.lout = lout; P.Ci = Ci;
   P.h_start = ah.start; P.h_size = ah.size; P.h_w = (const float*)ah.w; P.h_pitch = ah.pitch;
   P.w_start = aw.start; P.w_size = aw.size; P.w_w = (const float*)aw.w; P.w_pitch = aw.pitch;
   P.in_h = (int)ah.n_in; P.in_wf = (int)(aw.n_in * Ci); P.out_h = (int)ah.n_out; P.out_wf = (int)(aw.n_out * Ci);
@@ -272,7 +279,7 @@ int launch_tile(const void* in, int in_dtype, const Layout& lin, void* out, cons
     nc = std::max<int64_t>(nc, ((int64_t)aw.h_start[x1] + aw.h_size[x1] - aw.h_start[x0]) * Ci);
   }
   if (nc > 4096) return fail(AA_ERR_UNSUPPORTED, "tile: input patch too large; use the streaming/general path");
-  P.vec_store = (((uintptr_t)out) % 16 == 0) && (lout.stride_h % 4 == 0) && (lout.stride_n % 4 == 0) &&
+  P.vec_store = (((uintptr_t)out) % (epi.u8 ? 4 : 16) == 0) && (lout.stride_h % 4 == 0) && (lout.stride_n % 4 == 0) &&
                 (lout.Cp == 1 || lout.stride_p % 4 == 0);
   if (in_dtype == AA_F32) return launch_in<float>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream);
   return launch_in<uint8_t>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream);

@@ -51,7 +51,8 @@ void common_check(at::IntArrayRef input_size, at::IntArrayRef output_size) {
               ") output (H: ", output_size[0], ", W: ", output_size[1], ")");
 }
 
-at::Tensor forward_common(const at::Tensor& input, at::IntArrayRef output_size, bool align_corners, int filter, int64_t flags) {
+at::Tensor forward_common(const at::Tensor& input, at::IntArrayRef output_size, bool align_corners, int filter, int64_t flags,
+                          bool out_u8 = false) {
   TORCH_CHECK(input.is_cuda(), "aa_interp_b200: input must be a CUDA tensor (this build has no CPU fallback)");
   common_check(input.sizes(), output_size);
   // Allow for empty batch size but not other dimensions (aa_interpolation_impl.h:747-750)
@@ -59,7 +60,8 @@ at::Tensor forward_common(const at::Tensor& input, at::IntArrayRef output_size, 
               "Non-empty 4D data tensor expected but got a tensor with sizes ", input.sizes());
   const auto fmt = input.suggest_memory_format();
   const at::Tensor x = input.contiguous(fmt);
-  const auto out_dtype = x.scalar_type() == at::kDouble ? at::kDouble : at::kFloat;
+  TORCH_CHECK(!out_u8 || x.scalar_type() != at::kDouble, "uint8 output needs a uint8 or float32 input");
+  const auto out_dtype = out_u8 ? at::kByte : (x.scalar_type() == at::kDouble ? at::kDouble : at::kFloat);
   to_aa_dtype(x.scalar_type());
   at::Tensor out = at::empty({x.size(0), x.size(1), output_size[0], output_size[1]},
                              x.options().dtype(out_dtype).memory_format(fmt));
@@ -101,6 +103,10 @@ at::Tensor nearest_forward(const at::Tensor& i, at::IntArrayRef o, bool a) { ret
 at::Tensor forward_with_flags(const at::Tensor& i, at::IntArrayRef o, bool a, int64_t filter, int64_t flags) {
   return forward_common(i, o, a, (int)filter, flags);
 }
+// fused epilogue: clamp to [0,255] + truncate (reference caller, test.py:71-75) or round to nearest -> uint8
+at::Tensor forward_u8(const at::Tensor& i, at::IntArrayRef o, bool a, int64_t filter, bool round_nearest) {
+  return forward_common(i, o, a, (int)filter, round_nearest ? AA_FLAG_ROUND_NEAREST : 0, /*out_u8=*/true);
+}
 at::Tensor linear_backward(const at::Tensor& g, at::IntArrayRef o, at::IntArrayRef i, bool a) {
   return backward_common(g, o, i, a, AA_FILTER_TRIANGLE, false);
 }
@@ -125,4 +131,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("nearest_backward", &nearest_backward, "Anti-Aliased box Interpolation backward: true adjoint (sm_100a)");
   m.def("linear_backward_nonaa", &linear_backward_nonaa, "The reference's literal (non-antialiased) linear backward");
   m.def("forward_with_flags", &forward_with_flags, "forward(input, output_size, align_corners, filter, AA_FLAG_*)");
+  m.def("forward_u8", &forward_u8, "forward(input, output_size, align_corners, filter, round_nearest) -> uint8 (fused clamp + round)");
 }

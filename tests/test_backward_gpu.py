@@ -128,3 +128,23 @@ def test_backward_no_out_of_bounds_access(cuda):
                 assert (ob[:pad] == -12345.0).all() and (ob[pad + n_out:] == -12345.0).all()
                 want = O.backward_adjoint(src.numpy(), shape, mode, False)
                 np.testing.assert_allclose(gi.cpu().numpy(), want, rtol=1e-5, atol=1e-4)
+
+
+def test_custom_op_compile_and_autograd(cuda):
+    """torch.ops.aa_b200.resize: fake kernel + autograd formula; traces under torch.compile without graph breaks."""
+    import interpolate_antialiasing_b200 as aa  # noqa: F401  (registers the op)
+    torch.manual_seed(0)
+    x = torch.rand((2, 3, 64, 96), device=cuda, requires_grad=True)
+    y = torch.ops.aa_b200.resize(x, [16, 24], "bilinear", False)
+    y.square().sum().backward()
+    xr = x.detach().clone().requires_grad_(True)
+    yr = torch.nn.functional.interpolate(xr, size=(16, 24), mode="bilinear", antialias=True, align_corners=False)
+    yr.square().sum().backward()
+    assert torch.allclose(y, yr, rtol=1e-5, atol=1e-5) and torch.allclose(x.grad, xr.grad, rtol=1e-4, atol=1e-5)
+    torch.library.opcheck(torch.ops.aa_b200.resize.default, (x.detach(), [16, 24], "bilinear", False),
+                          test_utils=("test_schema", "test_faketensor"))
+
+    def f(t):
+        return torch.ops.aa_b200.resize(t * 2.0, [16, 24], "bicubic", False).sum()
+    fc = torch.compile(f, fullgraph=True, backend="aot_eager")
+    assert torch.allclose(fc(x.detach()), f(x.detach()))

@@ -270,3 +270,34 @@ def test_cuda_graph_capture_and_replay(cuda):
     torch.cuda.synchronize()
     _close(out.cpu().numpy(), O.forward(x.cpu().numpy(), (196, 320), "linear", False))
     np.testing.assert_allclose(gin.cpu().numpy(), O.backward_adjoint(go.cpu().numpy(), x.shape, "linear", False), rtol=1e-5, atol=1e-4)
+
+
+def test_fused_uint8_output(cuda, photo):
+    """clamp + round + uint8 store fused into the kernels (all three forward kernels)."""
+    from PIL import Image
+    from interpolate_antialiasing_b200 import capi
+    img = Image.fromarray(photo)
+    xu8 = torch.from_numpy(photo.transpose(2, 0, 1)[None].copy()).to(cuda)
+    xs = {False: xu8, True: xu8.contiguous(memory_format=torch.channels_last)}
+    for (w, h) in SIZES:
+        for mode, resample, max_tol in (("linear", Image.BILINEAR, 1.0), ("cubic", Image.BICUBIC, 20.0)):
+            pil = np.asarray(img.resize((w, h), resample=resample)).transpose(2, 0, 1).astype(np.int32)
+            want_f = np.clip(O.forward(xu8.float().cpu().numpy(), (h, w), mode, False)[0], 0, 255)
+            for cl in (False, True):
+                for flags in (capi.FLAG_AUTO, capi.FLAG_FORCE_GENERAL):
+                    # truncation = the reference caller's clamp + .byte() (test.py:71-75)
+                    y = capi.resize_forward(xs[cl], (h, w), mode, False, flags, out_u8=True)
+                    assert y.dtype == torch.uint8
+                    d = np.abs(y[0].cpu().numpy().astype(np.int32) - want_f.astype(np.uint8).astype(np.int32))
+                    assert d.max() <= 1 and (d != 0).mean() < 2e-3, (w, h, mode, cl, flags, d.max(), (d != 0).mean())
+                    if flags == capi.FLAG_FORCE_GENERAL:
+                        assert d.max() == 0  # bit-exact float path -> identical bytes
+                    # round to nearest = PIL's convention: closer to PIL than truncation
+                    yr = capi.resize_forward(xs[cl], (h, w), mode, False, flags | capi.FLAG_ROUND_NEAREST, out_u8=True)
+                    e = np.abs(yr[0].cpu().numpy().astype(np.int32) - pil)
+                    assert e.max() <= max_tol and e.mean() < (0.25 if mode == "linear" else 0.6), (w, h, mode, e.max(), e.mean())
+    # float32 input -> uint8 output through the torch extension
+    import interpolate_antialiasing_b200 as aa
+    y = aa.resize_to_uint8(xu8.float(), (196, 320), "bilinear", False, round_nearest=False)
+    want = np.clip(O.forward(xu8.float().cpu().numpy(), (196, 320), "linear", False), 0, 255).astype(np.uint8)
+    assert np.abs(y.cpu().numpy().astype(np.int32) - want.astype(np.int32)).max() <= 1
