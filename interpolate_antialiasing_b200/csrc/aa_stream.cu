@@ -169,20 +169,20 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
   }
 }
 
-template <int A, int VEC, typename in_t>
+template <int A, int VEC, typename in_t, int NT_>
 struct Cfg {
-  static constexpr int NT = 256;
+  static constexpr int NT = NT_;  // 256, or 128 when a whole row fits 128 threads (narrow images)
   static constexpr int U = 4;
   static constexpr int TG = 4;  // buffered rows that trigger a horizontal phase
-  // register budget: 64/thread (4 CTAs/SM) when the accumulators are few, else 2-3 CTAs/SM
-  static constexpr int MINB = (A * VEC <= 12) ? 4 : ((A * VEC <= 32) ? 3 : 2);
+  // register budget: 64/thread when the accumulators are few (4 CTAs/SM at 256 threads), else fewer CTAs
+  static constexpr int MINB = ((A * VEC <= 12) ? 4 : ((A * VEC <= 32) ? 3 : 2)) * (256 / NT_);
 };
 
-template <int A, int VEC, typename in_t>
+template <int A, int VEC, typename in_t, int NT_ = 256>
 int launch_cfg(SParams& P, const AxisTables* th, const AxisTables* tw, int device, cudaStream_t stream) {
-  using C = Cfg<A, VEC, in_t>;
+  using C = Cfg<A, VEC, in_t, NT_>;
   auto kern = aa_stream_kernel<A, VEC, in_t, C::NT, C::U, C::MINB>;
-  const PlanKey key{th, tw, P.Ci, (A << 8) | (VEC << 2) | (int)sizeof(in_t) % 4};
+  const PlanKey key{th, tw, P.Ci, (NT_ << 16) | (A << 8) | (VEC << 2) | (int)sizeof(in_t) % 4};
   Plan pl;
   if (!plan_lookup(key, &pl)) {
     P.in_pitch = 0;
@@ -215,6 +215,8 @@ int launch_cfg(SParams& P, const AxisTables* th, const AxisTables* tw, int devic
 template <int A>
 int launch_A(SParams& P, int in_dtype, int vec, const AxisTables* th, const AxisTables* tw, int device, cudaStream_t stream) {
   if (in_dtype == AA_F32) {
+    // narrow rows: a 128-thread CTA covers the whole row, so no lanes idle through the vertical pass
+    if (vec == 4 && tw->in * P.Ci <= 128 * 4) return launch_cfg<A, 4, float, 128>(P, th, tw, device, stream);
     if (vec == 4) return launch_cfg<A, 4, float>(P, th, tw, device, stream);
     if (vec == 2) return launch_cfg<A, 2, float>(P, th, tw, device, stream);
     return launch_cfg<A, 1, float>(P, th, tw, device, stream);
