@@ -301,3 +301,33 @@ def test_fused_uint8_output(cuda, photo):
     y = aa.resize_to_uint8(xu8.float(), (196, 320), "bilinear", False, round_nearest=False)
     want = np.clip(O.forward(xu8.float().cpu().numpy(), (196, 320), "linear", False), 0, 255).astype(np.uint8)
     assert np.abs(y.cpu().numpy().astype(np.int32) - want.astype(np.int32)).max() <= 1
+
+
+def test_extreme_shapes(cuda):
+    """Very large scale factors in both directions, degenerate axes, odd widths that defeat every vector
+    width, and windows longer than one strip: every case must land on SOME kernel and match the oracle."""
+    from interpolate_antialiasing_b200 import capi
+    g = torch.Generator().manual_seed(11)
+    cases = [
+        ((1, 1, 2048, 2048), (4, 4)),        # K = 1025 taps: a single window is wider than a strip
+        ((1, 3, 1000, 37), (3, 50)),         # huge down in H, up in W
+        ((1, 2, 8, 8), (128, 200)),          # 16x / 25x upsampling
+        ((2, 3, 33, 907), (9, 111)),         # odd width: scalar loads
+        ((1, 4, 300, 5), (7, 5)),            # identity in W, down in H
+        ((1, 3, 5, 4097), (5, 13)),          # identity in H, 315x down in W
+        ((1, 1, 1, 4096), (1, 64)), ((1, 1, 4096, 1), (64, 1)),
+        ((1, 5, 64, 64), (17, 23)),          # C = 5 channels_last (odd interleave)
+    ]
+    for shape, osize in cases:
+        for mode in ("linear", "cubic", "nearest"):
+            x = torch.rand(shape, generator=g) * 255
+            want = O.forward(x.numpy(), osize, mode, False)
+            for cl in (False, True):
+                for dt in (torch.float32, torch.uint8):
+                    xs = x.to(dt)
+                    wantd = want if dt == torch.float32 else O.forward(xs.float().numpy(), osize, mode, False)
+                    xc = xs.to(cuda)
+                    if cl:
+                        xc = xc.contiguous(memory_format=torch.channels_last)
+                    y = _run(capi, xc, osize, mode, False, capi.FLAG_AUTO)
+                    _close(y.cpu().numpy(), wantd)
