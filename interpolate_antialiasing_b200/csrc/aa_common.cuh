@@ -61,10 +61,11 @@ struct AxisTables {
   int32_t* omin = nullptr;   // [in]
   int32_t* osize = nullptr;  // [in]
   void* wT = nullptr;        // [in*KT]  float | double
-  // streaming slot tables (float only; built lazily for a given A)
-  int slot_A = 0;            // number of rotating accumulator slots
+  // per-input-row records of the streaming kernel's vertical pass (float only; built on first use)
+  int slot_A = 0;            // accumulators per element = max(3, kt_max)
   int slot_RS = 0;           // record stride in 32-bit words = roundup4(A+1)
-  float* slot = nullptr;     // [in][RS]: A weights by slot (o % A), then (first_flush_o | nflush<<24)
+  float* slot = nullptr;     // [in][RS]: wT[y][0..A) ordered by age (k-th oldest open output row), then
+                             //           (first_flush_o | nflush<<24)
   // host mirrors of the integer tables (for launch planning)
   std::vector<int32_t> h_xmin, h_xsize, h_omin, h_osize;
   ~AxisTables();
@@ -73,7 +74,7 @@ struct AxisTables {
 // Returns the cached tables, building them on `stream` on a miss (one sync on a miss only).
 int get_axis_tables(int device, int64_t in, int64_t out, int filter, int align, int dtype,
                     cudaStream_t stream, std::shared_ptr<AxisTables>* result);
-// Makes sure t->slot exists for at least `A` slots (A in {3,4,5,6,8}); may launch one tiny kernel.
+// Makes sure t->slot exists for `A` accumulators (A in 3..6); launches one tiny kernel on first use.
 int ensure_slot_tables(AxisTables* t, int A, cudaStream_t stream);
 int clear_table_cache();
 // Host-only K computation (no device), same arithmetic as the table kernel.
@@ -135,7 +136,7 @@ int launch_general(const void* in, int in_dtype, const Layout& lin, void* out, i
 int launch_tile(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout,
                 const BandedAxis& ah, const BandedAxis& aw, int kh_max, int kw_max, OutEpi epi, cudaStream_t stream);
 
-// Streaming fused kernel (downsampling in both axes, f32/u8 in, f32 out).  Returns
+// Streaming fused kernel (downsampling in H, any scale in W; f32/u8 in, f32/u8 out).  Returns
 // AA_ERR_UNSUPPORTED when not eligible so the caller can fall back to launch_general.
 int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout,
                   AxisTables* th, AxisTables* tw, int64_t H, int64_t W, int64_t oH, int64_t oW,

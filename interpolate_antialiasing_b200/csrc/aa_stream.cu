@@ -13,13 +13,15 @@
 //     accumulators per element, ordered by age: acc[k] collects the k-th oldest open output row.
 //     The per-row record {wT[y][0..A), first_flush_oy | nflush<<24} is warp-uniform (one 16/32-byte
 //     broadcast load).
+//     The FMAs are packed FFMA2 (two fp32 FMAs per issue slot, scalar weight broadcast).
 //   * When an output row's window ends, its accumulator (one vertically-filtered row, still at full
-//     input width) is flushed to shared memory.  Every G flushed rows the CTA runs the HORIZONTAL
-//     filter as a gather over the shared-memory rows (weights staged in shared memory, each weight
-//     reused for RPT rows) and writes G output rows with coalesced stores.
+//     input width) is flushed to shared memory.  Once >= tg rows are buffered the CTA runs the
+//     HORIZONTAL filter as a gather over the shared-memory rows (aa_stream_common.cuh: per-strip weight
+//     tables in shared memory, pairs of adjacent output columns x 4 rows per thread for wide strips)
+//     and writes the output rows with coalesced stores (optionally clamped/rounded to uint8).
 //   * Work is split stream-K style: the (plane, column strip, output row) space is cut into
-//     gridDim.x equal contiguous ranges, one per persistent CTA; a CTA that starts mid-plane re-reads
-//     only the <= 2*support_h halo rows of its first window.
+//     gridDim.x equal contiguous ranges; a CTA that starts mid-plane re-reads only the
+//     <= 2*support_h halo rows of its first window.
 //
 // Order of the passes is V then H (the reference is H then V).  Both orders evaluate the same
 // separable sum with fp32 rounding of the intermediate; the difference is pure rounding
@@ -36,7 +38,7 @@ namespace aa {
 using namespace stream_detail;
 namespace {
 
-// A     rotating accumulator slots (>= max outputs covering one input row)
+// A     accumulators per element, ordered by age (>= max output rows one input row contributes to)
 // VEC   flat elements per thread per row
 // NT    threads per CTA
 // U     input rows in flight per thread
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
   extern __shared__ __align__(16) float smem[];
   constexpr int RPT = 4;
   constexpr int VW = NT * VEC;  // row pitch of Vs in floats (== P.vw)  // rows per thread in the horizontal phase
-  constexpr int RS4 = (A + 1 + 3) / 4;  // float4 per slot record
+  constexpr int RS4 = (A + 1 + 3) / 4;  // float4 per row record
   using RawT = typename Raw<in_t, VEC>::T;
   constexpr int RN = Raw<in_t, VEC>::N;
   float* Vs = smem;                                  // [vr][vw]
@@ -285,7 +287,7 @@ int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, co
     case 5: return launch_A<5>(P, in_dtype, vec, th, tw, th->device, stream);
     case 6: return launch_A<6>(P, in_dtype, vec, th, tw, th->device, stream);
   }
-  return fail(AA_ERR_UNSUPPORTED, "stream: unsupported slot count");
+  return fail(AA_ERR_UNSUPPORTED, "stream: unsupported accumulator count");
 }
 
 }  // namespace aa
