@@ -1,0 +1,75 @@
+"""Randomised parity fuzz on a GPU box: random shapes / scales / layouts / dtypes / paths against the oracle.
+usage: python scripts/fuzz_parity.py [seconds] [seed]"""
+import os, sys, time, random
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from interpolate_antialiasing_b200 import capi
+from oracle import aa_oracle as O
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+rnd = random.Random(seed)
+g = torch.Generator().manual_seed(seed)
+dev = torch.device("cuda", 0)
+t0 = time.time()
+n = fails = 0
+paths = {"auto": capi.FLAG_AUTO, "stream": capi.FLAG_FORCE_STREAM, "tma": capi.FLAG_FORCE_STREAM | capi.FLAG_STREAM_TMA,
+         "general": capi.FLAG_FORCE_GENERAL}
+stats = {k: 0 for k in paths}
+while time.time() - t0 < budget:
+    C = rnd.choice([1, 1, 2, 3, 3, 4, 5])
+    N = rnd.choice([1, 1, 2, 3])
+    H = rnd.choice([rnd.randint(1, 40), rnd.randint(40, 300), rnd.randint(300, 700)])
+    W = rnd.choice([rnd.randint(1, 40), rnd.randint(40, 300), rnd.randint(300, 1400), 4 * rnd.randint(10, 300), 8 * rnd.randint(10, 200)])
+    def pick(n_in):
+        s = rnd.choice([0.05, 0.125, 0.2, 0.25, 0.33, 0.5, 0.6, 0.75, 0.9, 1.0, 1.1, 1.5, 2.0, 3.0, rnd.uniform(0.03, 3.0)])
+        return max(1, min(2000, round(n_in * s)))
+    oH, oW = pick(H), pick(W)
+    if N * C * (H * W + oH * oW) > 6e6:
+        continue
+    mode = rnd.choice(["linear", "linear", "cubic", "cubic", "nearest"])
+    align = rnd.random() < 0.25
+    cl = rnd.random() < 0.5
+    dt = rnd.choice([torch.float32, torch.float32, torch.uint8, torch.float64])
+    x = (torch.rand((N, C, H, W), generator=g, dtype=torch.float64) * 255).to(dt)
+    ref_in = x.double().numpy() if dt == torch.float64 else x.float().numpy()
+    want = O.forward(ref_in, (oH, oW), mode, align)
+    xc = x.to(dev)
+    if cl:
+        xc = xc.contiguous(memory_format=torch.channels_last)
+    for pname, fl in paths.items():
+        if dt == torch.float64 and pname in ("stream", "tma"):
+            continue
+        try:
+            y = capi.resize_forward(xc, (oH, oW), mode, align, fl)
+            torch.cuda.synchronize()
+        except capi.AAError as e:
+            if "-2" in str(e) and pname in ("stream", "tma"):
+                continue
+            print("ERROR", pname, (N, C, H, W), (oH, oW), mode, align, cl, dt, e); fails += 1; continue
+        got = y.cpu().numpy()
+        n += 1; stats[pname] += 1
+        if pname == "general":
+            ok = np.array_equal(got, want)
+        else:
+            tol = (1e-3 + 1e-5 * np.abs(want)) if dt != torch.float64 else (1e-9 + 1e-12 * np.abs(want))
+            ok = bool(np.all(np.abs(got.astype(np.float64) - want) <= tol))
+        if not ok or not np.isfinite(got).all():
+            fails += 1
+            print("MISMATCH", pname, (N, C, H, W), (oH, oW), mode, align, cl, dt, float(np.abs(got.astype(np.float64) - want).max()))
+    # backward (true adjoint) on a fraction of cases
+    if dt != torch.uint8 and rnd.random() < 0.4:
+        go = torch.rand((N, C, oH, oW), generator=g, dtype=torch.float64).to(dt)
+        wantg = O.backward_adjoint(go.numpy(), (N, C, H, W), mode, align)
+        gc = go.to(dev)
+        if cl:
+            gc = gc.contiguous(memory_format=torch.channels_last)
+        gi = capi.resize_backward(gc, (N, C, H, W), mode, align)
+        torch.cuda.synchronize()
+        n += 1
+        if not np.allclose(gi.cpu().numpy(), wantg, rtol=1e-5, atol=1e-4 if dt == torch.float32 else 1e-11):
+            fails += 1
+            print("BWD MISMATCH", (N, C, H, W), (oH, oW), mode, align, cl, dt, float(np.abs(gi.cpu().numpy() - wantg).max()))
+print(f"fuzz: {n} checks in {time.time() - t0:.0f}s, {fails} failures, per path {stats}")
+sys.exit(1 if fails else 0)

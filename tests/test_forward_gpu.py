@@ -331,3 +331,13 @@ def test_extreme_shapes(cuda):
                         xc = xc.contiguous(memory_format=torch.channels_last)
                     y = _run(capi, xc, osize, mode, False, capi.FLAG_AUTO)
                     _close(y.cpu().numpy(), wantd)
+
+
+def test_random_fuzz_all_paths(cuda):
+    """20 s of scripts/fuzz_parity.py: random shapes / scales / layouts / dtypes through every forward path
+    (general path bit-exact, fast paths within tolerance) and the backward, against the oracle."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_parity.py"), "20", "7"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "0 failures" in r.stdout
