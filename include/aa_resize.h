@@ -47,7 +47,9 @@ typedef enum aa_filter {
 typedef enum aa_dtype {
   AA_U8 = 0,  /* input only: the uint8 -> float cast the reference's caller does (test.py:55,67) is fused */
   AA_F32 = 1,
-  AA_F64 = 2
+  AA_F64 = 2,
+  AA_F16 = 3, /* output only, through aa_resize_forward_ex */
+  AA_BF16 = 4 /* output only, through aa_resize_forward_ex */
 } aa_dtype;
 
 /* execution-path selector for aa_resize_forward (flags argument) */
@@ -121,6 +123,20 @@ int aa_clear_table_cache(void);
  * n, c must match; in and out must be in the same memory format.  n == 0 is a no-op. */
 int aa_resize_forward(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter,
                       int align_corners, uint32_t flags, void* cuda_stream);
+
+/* Decode-adjacent fused epilogue (the step after this path in an input pipeline; not in the reference:
+ * there the caller would run `.permute()`, `(x/255 - mean)/std` and `.half()` as separate passes after
+ * proto_downsample, test.py:52-75).  Same as aa_resize_forward, plus, fused into the output stores:
+ *   - per-channel affine  v*scale[c] + bias[c]   (normalize != 0; c < 4),
+ *   - out->dtype AA_F16 / AA_BF16 / AA_F32 / AA_U8,
+ *   - a channels_first (planar) `out` for a channels_last `in` (HWC uint8 from a JPEG decoder -> CHW). */
+typedef struct aa_epilogue {
+  int32_t normalize;
+  float scale[4];
+  float bias[4];
+} aa_epilogue;
+int aa_resize_forward_ex(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align_corners,
+                         uint32_t flags, const aa_epilogue* epilogue, void* cuda_stream);
 
 /* grad_in = Wh^T * grad_out * Ww : the true adjoint of aa_resize_forward, gather form, no atomics,
  * no zero-fill pass.  Replaces ti_upsample_bilinear2d_backward_cpu,

@@ -18,7 +18,7 @@ from . import capi
 from ._build_ext import EXT, EXT_NAME, LIB
 
 __all__ = ["load", "linear_forward", "cubic_forward", "nearest_forward", "linear_backward", "cubic_backward",
-           "nearest_backward", "linear_backward_nonaa", "forward_with_flags", "resize_to_uint8", "AAResize", "aa_resize", "capi"]
+           "nearest_backward", "linear_backward_nonaa", "forward_with_flags", "resize_to_uint8", "decode_resize_normalize", "AAResize", "aa_resize", "capi"]
 
 _ext = None
 
@@ -76,6 +76,19 @@ def resize_to_uint8(input, output_size, mode="bilinear", align_corners=False, ro
     """uint8/float32 in -> uint8 out with the clamp + round epilogue fused into the kernel's store
     (round_nearest=False reproduces the reference harness' clamp + `.byte()` truncation, test.py:71-75)."""
     return load().forward_u8(input, list(output_size), align_corners, capi.FILTERS[mode], round_nearest)
+
+
+def decode_resize_normalize(x_hwc_u8, output_size, mean, std, mode="bilinear", out_dtype=None, align_corners=False):
+    """Decode-adjacent fused op: [N,H,W,C] uint8 (as a JPEG decoder emits) -> anti-aliased
+    resize -> (x/255 - mean)/std -> [N,C,oH,oW] contiguous float16/bfloat16/float32, all in ONE kernel."""
+    import torch
+    assert x_hwc_u8.dim() == 4 and x_hwc_u8.is_cuda
+    N, H, W, C = x_hwc_u8.shape
+    x = x_hwc_u8.permute(0, 3, 1, 2)  # a channels_last NCHW view of the same memory, no copy
+    out = torch.empty((N, C, int(output_size[0]), int(output_size[1])), dtype=out_dtype or torch.float16, device=x.device)
+    scale = [1.0 / (255.0 * s) for s in std]
+    bias = [-m / s for m, s in zip(mean, std)]
+    return capi.resize_forward_ex(x, output_size, mode, out, scale, bias, align_corners)
 
 
 from .functional import AAResize, aa_resize  # noqa: E402

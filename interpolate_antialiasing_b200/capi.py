@@ -10,13 +10,13 @@ import os
 from ._build_ext import LIB
 
 BOX, TRIANGLE, CUBIC = 0, 1, 2
-U8, F32, F64 = 0, 1, 2
+U8, F32, F64, F16, BF16 = 0, 1, 2, 3, 4
 FLAG_AUTO, FLAG_FORCE_GENERAL, FLAG_FORCE_STREAM, FLAG_STREAM_TMA, FLAG_STREAM_LDG, FLAG_ROUND_NEAREST = 0, 1, 2, 4, 8, 32
 FILTERS = {"nearest": BOX, "box": BOX, "bilinear": TRIANGLE, "linear": TRIANGLE, "bicubic": CUBIC, "cubic": CUBIC}
 
 EXPORTS = [
     "aa_abi_version", "aa_last_error", "aa_interp_size", "aa_build_tables", "aa_warm_tables",
-    "aa_clear_table_cache", "aa_resize_forward", "aa_resize_backward",
+    "aa_clear_table_cache", "aa_resize_forward", "aa_resize_forward_ex", "aa_resize_backward",
     "aa_resize_backward_nonaa_bilinear", "aa_resize_forward_host", "aa_launch_count",
 ]
 
@@ -31,6 +31,10 @@ class TensorDesc(ctypes.Structure):
 class TablesDesc(ctypes.Structure):
     _fields_ = [("xmin", ctypes.c_void_p), ("xsize", ctypes.c_void_p), ("weights", ctypes.c_void_p),
                 ("interp_size", ctypes.c_int32)]
+
+
+class Epilogue(ctypes.Structure):
+    _fields_ = [("normalize", ctypes.c_int32), ("scale", ctypes.c_float * 4), ("bias", ctypes.c_float * 4)]
 
 
 class AAError(RuntimeError):
@@ -56,6 +60,7 @@ def lib():
         L.aa_build_tables.argtypes = [i64, i64, i32, i32, i32, i32, P(TablesDesc), vp]
         L.aa_warm_tables.argtypes = [i64, i64, i64, i64, i32, i32, i32, i32, vp]
         L.aa_resize_forward.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, u32, vp]
+        L.aa_resize_forward_ex.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, u32, P(Epilogue), vp]
         L.aa_resize_backward.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, u32, vp]
         L.aa_resize_backward_nonaa_bilinear.argtypes = [P(TensorDesc), P(TensorDesc), i32, vp]
         L.aa_resize_forward_host.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, u32]
@@ -72,7 +77,7 @@ def check(rc):
 
 def _dtype_code(t):
     import torch
-    return {torch.uint8: U8, torch.float32: F32, torch.float64: F64}[t.dtype]
+    return {torch.uint8: U8, torch.float32: F32, torch.float64: F64, torch.float16: F16, torch.bfloat16: BF16}[t.dtype]
 
 
 def desc(t, device=None):
@@ -127,6 +132,20 @@ def resize_forward(x, output_size, filter, align_corners=False, flags=FLAG_AUTO,
                           device=x.device, memory_format=torch.channels_last if cl else torch.contiguous_format)
     di, do = desc(x), desc(out)
     check(lib().aa_resize_forward(ctypes.byref(di), ctypes.byref(do), _filter(filter), int(align_corners), flags, _stream(x)))
+    return out
+
+
+def resize_forward_ex(x, output_size, filter, out, scale=None, bias=None, align_corners=False, flags=FLAG_AUTO):
+    """C-ABI forward with the decode-adjacent epilogue: `out` may be f16/bf16/f32/u8 and channels_first for a
+    channels_last `x`; scale/bias (per channel, <= 4) apply v*scale[c] + bias[c] at the store."""
+    e = Epilogue()
+    e.normalize = 1 if scale is not None else 0
+    for i in range(4):
+        e.scale[i] = float(scale[i]) if scale is not None and i < len(scale) else 1.0
+        e.bias[i] = float(bias[i]) if bias is not None and i < len(bias) else 0.0
+    di, do = desc(x), desc(out)
+    check(lib().aa_resize_forward_ex(ctypes.byref(di), ctypes.byref(do), _filter(filter), int(align_corners), flags,
+                                     ctypes.byref(e), _stream(x)))
     return out
 
 

@@ -53,7 +53,7 @@ int check_desc(const aa_tensor_desc* t, const char* name) {
                                     std::to_string(t->n) + ", " + std::to_string(t->c) + ", " + std::to_string(t->h) + ", " +
                                     std::to_string(t->w) + "]");
   if (t->n > 0 && !t->data) return fail(AA_ERR_INVALID, std::string(name) + ".data is null");
-  if (t->dtype != AA_U8 && t->dtype != AA_F32 && t->dtype != AA_F64) return fail(AA_ERR_INVALID, std::string(name) + ": bad dtype");
+  if (t->dtype < AA_U8 || t->dtype > AA_BF16) return fail(AA_ERR_INVALID, std::string(name) + ": bad dtype");
   return AA_OK;
 }
 int check_filter(int filter) {
@@ -83,19 +83,31 @@ __global__ void widen_i32_i64(const int32_t* __restrict__ a, int64_t* __restrict
 }
 
 int forward_impl(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align, uint32_t flags,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, const aa_epilogue* ex = nullptr) {
   int rc;
   if ((rc = check_desc(in, "input")) != AA_OK) return rc;
   if ((rc = check_desc(out, "output")) != AA_OK) return rc;
   if ((rc = check_filter(filter)) != AA_OK) return rc;
   if (in->n != out->n || in->c != out->c) return fail(AA_ERR_INVALID, "input and output must agree in n and c");
   if (in->device != out->device) return fail(AA_ERR_INVALID, "input and output must live on the same device");
+  if (in->dtype > AA_F64) return fail(AA_ERR_INVALID, "input dtype must be u8, f32 or f64");
   const int tdtype = in->dtype == AA_F64 ? AA_F64 : AA_F32;
   OutEpi epi;
-  epi.u8 = (out->dtype == AA_U8 && tdtype == AA_F32) ? 1 : 0;
   epi.round = (flags & AA_FLAG_ROUND_NEAREST) ? 1 : 0;
-  if (out->dtype != tdtype && !epi.u8)
-    return fail(AA_ERR_INVALID, "output dtype must be f32 (or u8 with the fused clamp/round epilogue) for u8/f32 inputs and f64 for f64 inputs");
+  if (tdtype == AA_F32) {
+    if (out->dtype == AA_U8) epi.kind = 1;
+    else if (ex && out->dtype == AA_F16) epi.kind = 2;
+    else if (ex && out->dtype == AA_BF16) epi.kind = 3;
+  }
+  if (out->dtype != tdtype && epi.kind == 0)
+    return fail(AA_ERR_INVALID, "output dtype must be f32 (or u8 with the fused clamp/round epilogue; f16/bf16 through "
+                                "aa_resize_forward_ex) for u8/f32 inputs and f64 for f64 inputs");
+  if (ex && ex->normalize) {
+    if (tdtype != AA_F32) return fail(AA_ERR_UNSUPPORTED, "normalisation epilogue: u8/f32 inputs only");
+    if (in->c > 4) return fail(AA_ERR_UNSUPPORTED, "normalisation epilogue: at most 4 channels");
+    epi.norm = 1;
+    for (int i = 0; i < 4; i++) { epi.scale[i] = ex->scale[i]; epi.bias[i] = ex->bias[i]; }
+  }
   if (in->n == 0) return AA_OK;  // empty batch is allowed (aa_interpolation_impl.h:747-750)
   Layout lin, lout;
   bool in_cl = false, out_cl = false;
@@ -104,7 +116,18 @@ int forward_impl(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter
   if (in_cl != out_cl) {
     // ambiguous input (e.g. c == 1): retry with the output's format
     if ((rc = classify_layout(*in, out_cl, &lin, &in_cl)) != AA_OK) return rc;
-    if (in_cl != out_cl) return fail(AA_ERR_UNSUPPORTED, "input and output must use the same memory format");
+  }
+  if (in_cl != out_cl) {
+    // decode-adjacent case: channels_last (HWC) input -> channels_first (planar) output, fused into the stores
+    if (!(ex && in_cl && !out_cl && tdtype == AA_F32))
+      return fail(AA_ERR_UNSUPPORTED, "input and output must use the same memory format (channels_last -> channels_first is "
+                                      "available through aa_resize_forward_ex)");
+    if (out->stride_c >= (1ll << 31) / (out->c > 0 ? out->c : 1)) return fail(AA_ERR_UNSUPPORTED, "planar output: plane stride too large");
+    epi.planar = 1;
+    epi.stride_c = (int)out->stride_c;
+    lout = Layout();
+    lout.planes = out->n; lout.Cp = 1; lout.Ci = (int)out->c; lout.stride_n = out->stride_n; lout.stride_p = 0;
+    lout.stride_h = (out->h == 1) ? out->w : out->stride_h;
   }
   DeviceGuard g(in->device);
   if (!g.ok) return cuda_fail(g.err, "cudaSetDevice");
@@ -217,6 +240,12 @@ int aa_resize_forward(const aa_tensor_desc* in, const aa_tensor_desc* out, int f
   return forward_impl(in, out, filter, align_corners, flags, (cudaStream_t)cuda_stream);
 }
 
+int aa_resize_forward_ex(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align_corners, uint32_t flags,
+                         const aa_epilogue* epilogue, void* cuda_stream) {
+  if (!epilogue) return fail(AA_ERR_INVALID, "aa_resize_forward_ex: epilogue is null (use aa_resize_forward)");
+  return forward_impl(in, out, filter, align_corners, flags, (cudaStream_t)cuda_stream, epilogue);
+}
+
 int aa_resize_backward(const aa_tensor_desc* gout, const aa_tensor_desc* gin, int filter, int align_corners, uint32_t flags,
                        void* cuda_stream) {
   int rc;
@@ -275,6 +304,7 @@ int aa_resize_forward_host(const aa_tensor_desc* in, const aa_tensor_desc* out, 
   const int dev = in->device;
   if (dev < 0 || dev >= 64) return fail(AA_ERR_INVALID, "bad device ordinal");
   const size_t ies = in->dtype == AA_U8 ? 1 : (in->dtype == AA_F32 ? 4 : 8);
+  if (out->dtype > AA_F64) return fail(AA_ERR_UNSUPPORTED, "host path: u8/f32/f64 outputs only");
   const size_t oes = out->dtype == AA_U8 ? 1 : (out->dtype == AA_F32 ? 4 : 8);
   const size_t img_in = (size_t)in->c * in->h * in->w, img_out = (size_t)out->c * out->h * out->w;
   if ((in->n > 1 && (size_t)in->stride_n != img_in) || (out->n > 1 && (size_t)out->stride_n != img_out))

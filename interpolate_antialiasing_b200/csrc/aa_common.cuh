@@ -95,23 +95,55 @@ struct Layout {
 int classify_layout(const aa_tensor_desc& t, bool prefer_channels_last, Layout* out, bool* is_channels_last);
 
 // ---- fused output epilogue --------------------------------------------------------------------
-// out dtype AA_U8: clamp to [0,255] then truncate (what the reference's caller does: torch.clamp +
-// .byte(), /root/reference/test.py:71-75) or, with AA_FLAG_ROUND_NEAREST, add 0.5 first (PIL's rounding).
+// kind 1 (uint8): clamp to [0,255] then truncate (what the reference's caller does: torch.clamp + .byte(),
+// /root/reference/test.py:71-75) or, with AA_FLAG_ROUND_NEAREST, add 0.5 first (PIL's rounding).
+// kinds 2/3 (fp16/bf16), `norm` (v*scale[c] + bias[c]) and `planar` (channels_first output from a
+// channels_last input) make up the decode-adjacent epilogue of aa_resize_forward_ex.
 struct OutEpi {
-  int u8 = 0;     // 1: store uint8
-  int round = 0;  // 1: round to nearest instead of truncating
+  int kind = 0;    // 0: float32, 1: uint8, 2: float16, 3: bfloat16
+  int round = 0;   // uint8: round to nearest instead of truncating
+  int planar = 0;  // 1: write channel planes (offset c*stride_c + ox) although rows are processed interleaved
+  int norm = 0;    // 1: v = v*scale[c] + bias[c]
+  int stride_c = 0;  // planar: elements between channel planes
+  float scale[4] = {1.f, 1.f, 1.f, 1.f};
+  float bias[4] = {0.f, 0.f, 0.f, 0.f};
+  // offset of output column (ox, c) inside one output row / plane set, and the step to (ox+1, c)
+  __host__ __device__ int coloff(int ox, int c, int Ci) const { return planar ? c * stride_c + ox : ox * Ci + c; }
+  __host__ __device__ int colstep(int Ci) const { return planar ? 1 : Ci; }
+  __host__ __device__ bool plain() const { return kind == 0 && !planar && !norm; }
+  // the decode-adjacent features need the GEN=true kernel instantiations (kept out of the default kernels so
+  // their register budgets are untouched)
+  __host__ __device__ bool generic() const { return planar || norm || kind >= 2; }
 };
+}  // namespace aa
 #ifdef __CUDACC__
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+namespace aa {
 __device__ __forceinline__ unsigned int aa_to_u8(float v, int round) {
   v = fminf(fmaxf(v, 0.f), 255.f);
   return (unsigned int)(round ? v + 0.5f : v);
 }
-// element store through a base pointer whose element type depends on the epilogue
-__device__ __forceinline__ void aa_store(void* base, int64_t idx, float v, const OutEpi e) {
-  if (e.u8) reinterpret_cast<uint8_t*>(base)[idx] = (uint8_t)aa_to_u8(v, e.round);
-  else reinterpret_cast<float*>(base)[idx] = v;
+// element store through a base pointer whose element type depends on the epilogue; c = channel of the element.
+// GEN=false knows only float32 / uint8 (the reference-facing surface); GEN=true adds normalisation and halves.
+template <bool GEN>
+__device__ __forceinline__ void aa_store(void* base, int64_t idx, float v, int c, const OutEpi& e) {
+  if constexpr (!GEN) {
+    if (e.kind == 1) reinterpret_cast<uint8_t*>(base)[idx] = (uint8_t)aa_to_u8(v, e.round);
+    else reinterpret_cast<float*>(base)[idx] = v;
+  } else {
+    if (e.norm) v = fmaf(v, e.scale[c & 3], e.bias[c & 3]);
+    switch (e.kind) {
+      case 0: reinterpret_cast<float*>(base)[idx] = v; break;
+      case 1: reinterpret_cast<uint8_t*>(base)[idx] = (uint8_t)aa_to_u8(v, e.round); break;
+      case 2: reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v); break;
+      default: reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v); break;
+    }
+  }
 }
+}  // namespace aa
 #endif
+namespace aa {
 
 // ---- kernels' host launchers ---------------------------------------------------------------
 struct BandedAxis {  // one axis of a banded separable apply: out index i reads in [start[i], start[i]+size[i])

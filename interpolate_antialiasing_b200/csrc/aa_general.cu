@@ -140,9 +140,10 @@ __global__ void __launch_bounds__(TW* NTY) aa_general_kernel(const GParams P) {
       const int64_t oy = oy0 + ty + r * NTY;
       if (oy < P.out_h) {
         if constexpr (sizeof(acc_t) == 4) {
-          if (P.epi.u8) {
-            const int64_t off = (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p + oy * P.lout.stride_h + of;
-            reinterpret_cast<uint8_t*>(P.out)[off] = (uint8_t)aa_to_u8((float)acc[r], P.epi.round);
+          if (!P.epi.plain()) {
+            const int64_t off = (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p + oy * P.lout.stride_h +
+                                P.epi.coloff((int)jx, c, Ci);
+            aa_store<true>(P.out, off, (float)acc[r], c, P.epi);
             continue;
           }
         }
@@ -252,8 +253,8 @@ int launch_general(const void* in, int in_dtype, const Layout& lin, void* out, i
                    OutEpi epi, cudaStream_t stream) {
   GParams P;
   P.in = in; P.out = out; P.epi = epi; P.lin = lin; P.lout = lout;
-  if (epi.u8) {
-    if (in_dtype == AA_F64) return fail(AA_ERR_UNSUPPORTED, "uint8 output needs u8 or f32 input");
+  if (!epi.plain()) {
+    if (in_dtype == AA_F64) return fail(AA_ERR_UNSUPPORTED, "the fused output epilogue needs u8 or f32 input");
     out_dtype = AA_F32;  // accumulate in f32, convert at the store
   }
   P.h_start = ah.start; P.h_size = ah.size; P.h_w = ah.w; P.h_pitch = ah.pitch;

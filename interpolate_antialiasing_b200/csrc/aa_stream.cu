@@ -45,7 +45,7 @@ namespace {
 // MINB  CTAs per SM the register allocation must allow
 // Shared memory holds up to P.vr vertically-filtered rows; the horizontal phase runs at the end of a
 // U-row batch once at least P.tg rows are buffered (host guarantees tg - 1 + max flushes per batch <= vr).
-template <int A, int VEC, typename in_t, int NT, int U, int MINB>
+template <int A, int VEC, typename in_t, int NT, int U, int MINB, bool GEN>
 __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
   extern __shared__ __align__(16) float smem[];
   constexpr int RPT = 4;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
     const int64_t yB = (int64_t)__ldg(P.xmin_h + oyB - 1) + __ldg(P.xsize_h + oyB - 1);
     const in_t* ip = (const in_t*)P.in + (plane / P.lin.Cp) * P.lin.stride_n + (plane % P.lin.Cp) * P.lin.stride_p + fmy + yA * stride_h;
     const float4* rp = reinterpret_cast<const float4*>(P.slot_h) + yA * RS4;
-    const int64_t op = (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p + (int64_t)ox0 * Ci;  // element offset
+    const int64_t op = (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p;  // element offset of the plane
     float* vdst = Vs + VEC * t;
 
     float acc[A][VEC];
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
     // horizontal filter over the buffered rows [gbase, gbase+cnt)
     auto hphase = [&]() {
       __syncthreads();
-      hphase_run<RPT, VW>(P, Vs, Wp, pinfo, op, strip_npc, role, gbase, cnt);
+      hphase_run<RPT, VW, GEN>(P, Vs, Wp, pinfo, op, strip_npc, role, gbase, cnt);
       __syncthreads();
       gbase += cnt;
       cnt = 0;
@@ -180,11 +180,17 @@ struct Cfg {
   static constexpr int MINB = ((A * VEC <= 12) ? 4 : ((A * VEC <= 32) ? 3 : 2)) * (256 / NT_);
 };
 
-template <int A, int VEC, typename in_t, int NT_ = 256>
+template <int A, int VEC, typename in_t, int NT_ = 256, bool GEN = false>
 int launch_cfg(SParams& P, const AxisTables* th, const AxisTables* tw, int device, cudaStream_t stream) {
   using C = Cfg<A, VEC, in_t, NT_>;
-  auto kern = aa_stream_kernel<A, VEC, in_t, C::NT, C::U, C::MINB>;
-  const PlanKey key{th, tw, P.Ci, (NT_ << 16) | (A << 8) | (VEC << 2) | (int)sizeof(in_t) % 4};
+  if constexpr (!GEN && NT_ == 256 && (VEC == 4 || (VEC == 8 && sizeof(in_t) == 1))) {
+    // decode-adjacent epilogue (normalise / half / planar): separate instantiations of the common shapes
+    if (P.epi.generic()) return launch_cfg<A, VEC, in_t, NT_, true>(P, th, tw, device, stream);
+  } else if constexpr (!GEN) {
+    if (P.epi.generic()) return fail(AA_ERR_UNSUPPORTED, "stream: generic epilogue not instantiated for this shape");
+  }
+  auto kern = aa_stream_kernel<A, VEC, in_t, C::NT, C::U, C::MINB, GEN>;
+  const PlanKey key{th, tw, P.Ci, (GEN ? (1 << 28) : 0) | (NT_ << 16) | (A << 8) | (VEC << 2) | (int)sizeof(in_t) % 4};
   Plan pl;
   if (!plan_lookup(key, &pl)) {
     P.in_pitch = 0;
@@ -257,7 +263,7 @@ int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, co
   if (in_dtype != AA_F32 && in_dtype != AA_U8) return fail(AA_ERR_UNSUPPORTED, "stream: input must be f32 or u8");
   if (th->dtype != AA_F32 || tw->dtype != AA_F32) return fail(AA_ERR_UNSUPPORTED, "stream: f32 tables only");
   if (th->kt_max > kMaxA) return fail(AA_ERR_UNSUPPORTED, "stream: too many output rows per input row (upsampling in H)");
-  if (oH >= (1 << 24) || W * lin.Ci >= (1ll << 30)) return fail(AA_ERR_UNSUPPORTED, "stream: size limits");
+  if (oH >= (1 << 24) || W * lin.Ci >= (1ll << 30) || tw->K >= (1 << 16) || lin.Ci > 2047) return fail(AA_ERR_UNSUPPORTED, "stream: size limits");
   // widest vector the addresses allow: base pointer, plane strides and row stride must all be aligned
   const int es = in_dtype == AA_F32 ? 4 : 1;
   auto aligned = [&](int vec) {

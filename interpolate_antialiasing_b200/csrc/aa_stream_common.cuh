@@ -133,8 +133,8 @@ template <int VEC> __device__ __forceinline__ void store_vec(float* dst, const f
 // thread computes a PAIR of adjacent columns (same channel) for RPT buffered rows: every Vs element it
 // loads feeds both columns, and the two weights arrive in one 64-bit load.  Per strip the kernel builds
 //   Wp[pair][KP]     float2 {w_a[j], w_b[j - shift]} zero padded, shift = xmin_b - xmin_a
-//   pinfo[pair*Ci+c] int4   {first tap's offset in a Vs row, pair*KP, union window length | has_b<<16,
-//                            flat output column of column a}
+//   pinfo[pair*Ci+c] int4   {first tap's offset in a Vs row, pair*KP, union window length | has_b<<16 | c<<20,
+//                            offset of column a inside an output row (OutEpi::coloff)}
 // so the phase itself needs no integer division and no per-column table lookups.
 struct HRole {        // which (row group, pair-column) items a thread owns; fixed per strip
   int rg0, rg_par;    // first row group and stride over row groups
@@ -168,7 +168,8 @@ __device__ __forceinline__ void strip_setup(const SParams& P, int t, int nthread
     for (int i = t; i < nox * Kw; i += nthreads) Ws[i] = __ldg(P.w_w + (int64_t)ox0 * Kw + i);
     for (int cf = t; cf < nox * Ci; cf += nthreads) {
       const int oxl = cf / Ci, c = cf - oxl * Ci;
-      pinfo[cf] = make_int4(__ldg(P.xmin_w + ox0 + oxl) * Ci + c - fl0, oxl * Kw, __ldg(P.xsize_w + ox0 + oxl), cf);
+      pinfo[cf] = make_int4(__ldg(P.xmin_w + ox0 + oxl) * Ci + c - fl0, oxl * Kw, __ldg(P.xsize_w + ox0 + oxl) | (c << 20),
+                            P.epi.coloff(ox0 + oxl, c, Ci));
     }
     *npc_out = nox * Ci;
     return;
@@ -191,17 +192,17 @@ __device__ __forceinline__ void strip_setup(const SParams& P, int t, int nthread
     const int xa = __ldg(P.xmin_w + oa);
     int len = __ldg(P.xsize_w + oa), hasb = 0;
     if (ob < ox1) { len = max(len, __ldg(P.xmin_w + ob) - xa + __ldg(P.xsize_w + ob)); hasb = 1; }
-    pinfo[pc] = make_int4(xa * Ci + c - fl0, p * KP, len | (hasb << 16), 2 * p * Ci + c);
+    pinfo[pc] = make_int4(xa * Ci + c - fl0, p * KP, len | (hasb << 16) | (c << 20), P.epi.coloff(oa, c, Ci));
   }
   *npc_out = np * Ci;
 }
 // Gather over the buffered rows [0, cnt) of Vs -> output rows gbase..gbase+cnt-1.  Trip counts are
 // warp-uniform (longest union window in the warp); past a lane's own window the weights read are the
 // zero padding and the data pointer stops advancing, so no element outside the true windows is touched.
-template <int RPT, int VW>
+template <int RPT, int VW, bool GEN>
 __device__ __forceinline__ void hphase_run_pairs(const float* __restrict__ Vs, const float2* __restrict__ Wp,
                                            const int4* __restrict__ pinfo, void* __restrict__ op, int64_t op_off,
-                                           const OutEpi epi, int64_t out_stride_h, int Ci, int npc, const HRole role, int gbase,
+                                           const OutEpi& epi, int64_t out_stride_h, int Ci, int npc, const HRole role, int gbase,
                                            int cnt) {
   const int nrg = (cnt + RPT - 1) / RPT;
   for (int rg = role.rg0; rg < nrg; rg += role.rg_par) {
@@ -228,12 +229,13 @@ __device__ __forceinline__ void hphase_run_pairs(const float* __restrict__ Vs, c
       }
       if (act) {
         const int64_t dst = op_off + (int64_t)(gbase + rg * RPT) * out_stride_h + pi.w;
-        const bool hasb = (pi.z >> 16) != 0;
+        const bool hasb = ((pi.z >> 16) & 1) != 0;
+        const int c = pi.z >> 20, cstep = epi.colstep(Ci);
 #pragma unroll
         for (int r = 0; r < RPT; r++) {
           if (rg * RPT + r < cnt) {
-            aa_store(op, dst + (int64_t)r * out_stride_h, h[r].x, epi);
-            if (hasb) aa_store(op, dst + (int64_t)r * out_stride_h + Ci, h[r].y, epi);
+            aa_store<GEN>(op, dst + (int64_t)r * out_stride_h, h[r].x, c, epi);
+            if (hasb) aa_store<GEN>(op, dst + (int64_t)r * out_stride_h + cstep, h[r].y, c, epi);
           }
         }
       }
@@ -241,10 +243,10 @@ __device__ __forceinline__ void hphase_run_pairs(const float* __restrict__ Vs, c
   }
 }
 // single-column form (P.pairs == 0): one item = one flat output column x RPT rows, FFMA2 over row pairs
-template <int RPT, int VW>
+template <int RPT, int VW, bool GEN>
 __device__ __forceinline__ void hphase_run_single(const float* __restrict__ Vs, const float* __restrict__ Ws,
                                                   const int4* __restrict__ pinfo, void* __restrict__ op, int64_t op_off,
-                                                  const OutEpi epi, int64_t out_stride_h, int Ci, int nof, const HRole role,
+                                                  const OutEpi& epi, int64_t out_stride_h, int Ci, int nof, const HRole role,
                                                   int gbase, int cnt) {
   const int nrg = (cnt + RPT - 1) / RPT;
   for (int rg = role.rg0; rg < nrg; rg += role.rg_par) {
@@ -252,7 +254,7 @@ __device__ __forceinline__ void hphase_run_single(const float* __restrict__ Vs, 
       const int cf = cfb + (role.cf0 & 31);
       const bool act = cf < nof;
       const int4 ci = pinfo[act ? cf : 0];
-      const int xs = act ? ci.z : 1;
+      const int xs = act ? (ci.z & 0xfffff) : 1;
       const int xsm = __reduce_max_sync(0xffffffffu, xs);
       const float* wr = Ws + ci.y;
       const float* vp = Vs + (rg * RPT) * VW + ci.x;
@@ -272,19 +274,20 @@ __device__ __forceinline__ void hphase_run_single(const float* __restrict__ Vs, 
         vp += (j + 1 < xs) ? Ci : 0;
       }
       if (act) {
-        const int64_t dst = op_off + (int64_t)(gbase + rg * RPT) * out_stride_h + cf;
+        const int64_t dst = op_off + (int64_t)(gbase + rg * RPT) * out_stride_h + ci.w;
+        const int c = ci.z >> 20;
 #pragma unroll
         for (int r = 0; r < RPT; r++)
-          if (rg * RPT + r < cnt) aa_store(op, dst + (int64_t)r * out_stride_h, h[r], epi);
+          if (rg * RPT + r < cnt) aa_store<GEN>(op, dst + (int64_t)r * out_stride_h, h[r], c, epi);
       }
     }
   }
 }
-template <int RPT, int VW>
+template <int RPT, int VW, bool GEN>
 __device__ __forceinline__ void hphase_run(const SParams& P, const float* Vs, const float2* Wp, const int4* pinfo, int64_t op_off,
                                            int npc, const HRole role, int gbase, int cnt) {
-  if (P.pairs) hphase_run_pairs<RPT, VW>(Vs, Wp, pinfo, P.out, op_off, P.epi, P.lout.stride_h, P.Ci, npc, role, gbase, cnt);
-  else hphase_run_single<RPT, VW>(Vs, reinterpret_cast<const float*>(Wp), pinfo, P.out, op_off, P.epi, P.lout.stride_h, P.Ci, npc, role, gbase, cnt);
+  if (P.pairs) hphase_run_pairs<RPT, VW, GEN>(Vs, Wp, pinfo, P.out, op_off, P.epi, P.lout.stride_h, P.Ci, npc, role, gbase, cnt);
+  else hphase_run_single<RPT, VW, GEN>(Vs, reinterpret_cast<const float*>(Wp), pinfo, P.out, op_off, P.epi, P.lout.stride_h, P.Ci, npc, role, gbase, cnt);
 }
 // bytes of the strip tables (after Vs) for a plan
 inline size_t strip_table_bytes(const SParams& P) {

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
     const int64_t yA = __ldg(P.xmin_h + oyA);
     const int64_t yB = (int64_t)__ldg(P.xmin_h + oyB - 1) + __ldg(P.xsize_h + oyB - 1);
     const float4* rp = reinterpret_cast<const float4*>(P.slot_h) + yA * RS4;
-    const int64_t op = (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p + (int64_t)ox0 * Ci;  // element offset
+    const int64_t op = (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p;  // element offset of the plane
     float* vdst = Vs + VEC * t;
     const unsigned char* my_in = stage_base + (size_t)VEC * ES * t;  // + stage*R*in_pitch + i*in_pitch
 
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
     };
     auto hphase = [&]() {
       consumer_sync();
-      hphase_run<RPT, VW>(P, Vs, Wp, pinfo, op, strip_npc, role, gbase, cnt);
+      hphase_run<RPT, VW, false>(P, Vs, Wp, pinfo, op, strip_npc, role, gbase, cnt);
       consumer_sync();
       gbase += cnt;
       cnt = 0;
@@ -277,6 +277,7 @@ int launch_tma_A(SParams& P, int in_dtype, const AxisTables* th, const AxisTable
 }  // namespace
 
 int launch_stream_tma(SParams& P, int A, int in_dtype, const AxisTables* th, const AxisTables* tw, int device, cudaStream_t stream) {
+  if (P.epi.generic()) return fail(AA_ERR_UNSUPPORTED, "stream/tma: generic epilogue not instantiated");
   // cp.async.bulk needs 16-byte aligned global addresses and sizes: base, plane and row strides
   const int es = in_dtype == AA_F32 ? 4 : 1;
   const int64_t al = 16 / es;

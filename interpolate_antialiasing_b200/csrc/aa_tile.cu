@@ -46,7 +46,7 @@ struct TParams {
 
 template <typename in_t> __device__ __forceinline__ float ldf(const in_t* p) { return (float)__ldg(p); }
 
-template <int KH, int KW, int TY, typename in_t>
+template <int KH, int KW, int TY, bool GEN, typename in_t>
 __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
   constexpr int HR = (KH + 1 + 3) / 4;  // float4 per row record {w[KH], first T row}
   extern __shared__ __align__(16) float smem[];
@@ -166,9 +166,20 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
   // ---- stage 2: vertical pass + store
   const int ofv = of0 + 4 * tx;
   if (ofv < of1) {
-    int64_t dst = op + (int64_t)(oy0 + ty) * P.lout.stride_h + ofv;
+    int64_t dst = op + (int64_t)(oy0 + ty) * P.lout.stride_h;  // row base; column offsets below
     const int64_t dstep = (int64_t)NTY * P.lout.stride_h;
     const bool full = P.vec_store && (ofv + 4 <= of1);
+    int coff[4], cch[4];  // per-column output offset and channel (the generic epilogue may be planar / per-channel)
+#pragma unroll
+    for (int i = 0; i < 4; i++) { coff[i] = ofv + i; cch[i] = 0; }
+    if constexpr (GEN) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int oxi = (ofv + i) / Ci;
+        cch[i] = (ofv + i) - oxi * Ci;
+        coff[i] = P.epi.coloff(oxi, cch[i], Ci);
+      }
+    }
 #pragma unroll 2
     for (int oyl = ty; oyl < oy1 - oy0; oyl += NTY, dst += dstep) {
       float rec[HR * 4];
@@ -184,25 +195,23 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
         const float4 v = src[k * TXV];
         a.x = fmaf(v.x, rec[k], a.x); a.y = fmaf(v.y, rec[k], a.y); a.z = fmaf(v.z, rec[k], a.z); a.w = fmaf(v.w, rec[k], a.w);
       }
-      if (full) {
-        if (P.epi.u8) {
-          const unsigned int pk = aa_to_u8(a.x, P.epi.round) | (aa_to_u8(a.y, P.epi.round) << 8) |
-                                  (aa_to_u8(a.z, P.epi.round) << 16) | (aa_to_u8(a.w, P.epi.round) << 24);
-          *reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(P.out) + dst) = pk;
-        } else {
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + dst) = a;
-        }
+      if (!GEN && full && P.epi.kind == 0) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + dst + ofv) = a;
+      } else if (!GEN && full && P.epi.kind == 1) {
+        const unsigned int pk = aa_to_u8(a.x, P.epi.round) | (aa_to_u8(a.y, P.epi.round) << 8) |
+                                (aa_to_u8(a.z, P.epi.round) << 16) | (aa_to_u8(a.w, P.epi.round) << 24);
+        *reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(P.out) + dst + ofv) = pk;
       } else {
-        aa_store(P.out, dst, a.x, P.epi);
-        if (ofv + 1 < of1) aa_store(P.out, dst + 1, a.y, P.epi);
-        if (ofv + 2 < of1) aa_store(P.out, dst + 2, a.z, P.epi);
-        if (ofv + 3 < of1) aa_store(P.out, dst + 3, a.w, P.epi);
+        aa_store<GEN>(P.out, dst + coff[0], a.x, cch[0], P.epi);
+        if (ofv + 1 < of1) aa_store<GEN>(P.out, dst + coff[1], a.y, cch[1], P.epi);
+        if (ofv + 2 < of1) aa_store<GEN>(P.out, dst + coff[2], a.z, cch[2], P.epi);
+        if (ofv + 3 < of1) aa_store<GEN>(P.out, dst + coff[3], a.w, cch[3], P.epi);
       }
     }
   }
 }
 
-template <int KH, int KW, int TY, typename in_t>
+template <int KH, int KW, int TY, bool GEN, typename in_t>
 int launch_ty(TParams& P, int64_t planes, const BandedAxis& ah, size_t smem_limit, cudaStream_t stream) {
   constexpr int HR = (KH + 1 + 3) / 4;
   // exact row plan for this tile height from the host mirror
@@ -219,7 +228,7 @@ int launch_ty(TParams& P, int64_t planes, const BandedAxis& ah, size_t smem_limi
   const int64_t nblocks = (int64_t)P.tiles_x * P.tiles_y * planes;
   if (nblocks <= 0) return AA_OK;
   if (nblocks >= (1ll << 31)) return fail(AA_ERR_UNSUPPORTED, "tile: too many tiles");
-  auto kern = aa_tile_kernel<KH, KW, TY, in_t>;
+  auto kern = aa_tile_kernel<KH, KW, TY, GEN, in_t>;
   if (smem > 48 * 1024) AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)nblocks, NT, smem, stream>>>(P);
   AA_LAUNCH_CHECK("aa_tile_kernel");
@@ -232,11 +241,16 @@ int launch_k(TParams& P, int64_t planes, const BandedAxis& ah, int nc_max, cudaS
   pcp |= 1;  // odd pitch
   P.pcp = pcp;
   // tall tiles amortise the per-CTA setup when the patch stays small (upsampling-like gathers)
-  int rc = launch_ty<KH, KW, 64, in_t>(P, planes, ah, 40 * 1024, stream);
+  if (P.epi.generic()) {  // decode-adjacent epilogue: its own instantiations, two tile heights
+    int rg = launch_ty<KH, KW, 32, true, in_t>(P, planes, ah, 72 * 1024, stream);
+    if (rg != AA_ERR_UNSUPPORTED) return rg;
+    return launch_ty<KH, KW, 16, true, in_t>(P, planes, ah, 72 * 1024, stream);
+  }
+  int rc = launch_ty<KH, KW, 64, false, in_t>(P, planes, ah, 40 * 1024, stream);
   if (rc != AA_ERR_UNSUPPORTED) return rc;
-  rc = launch_ty<KH, KW, 32, in_t>(P, planes, ah, 72 * 1024, stream);
+  rc = launch_ty<KH, KW, 32, false, in_t>(P, planes, ah, 72 * 1024, stream);
   if (rc != AA_ERR_UNSUPPORTED) return rc;
-  return launch_ty<KH, KW, 16, in_t>(P, planes, ah, 72 * 1024, stream);
+  return launch_ty<KH, KW, 16, false, in_t>(P, planes, ah, 72 * 1024, stream);
 }
 
 template <int KH, typename in_t>
@@ -279,7 +293,7 @@ int launch_tile(const void* in, int in_dtype, const Layout& lin, void* out, cons
     nc = std::max<int64_t>(nc, ((int64_t)aw.h_start[x1] + aw.h_size[x1] - aw.h_start[x0]) * Ci);
   }
   if (nc > 4096) return fail(AA_ERR_UNSUPPORTED, "tile: input patch too large; use the streaming/general path");
-  P.vec_store = (((uintptr_t)out) % (epi.u8 ? 4 : 16) == 0) && (lout.stride_h % 4 == 0) && (lout.stride_n % 4 == 0) &&
+  P.vec_store = (((uintptr_t)out) % (epi.kind == 1 ? 4 : 16) == 0) && (lout.stride_h % 4 == 0) && (lout.stride_n % 4 == 0) &&
                 (lout.Cp == 1 || lout.stride_p % 4 == 0);
   if (in_dtype == AA_F32) return launch_in<float>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream);
   return launch_in<uint8_t>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream);

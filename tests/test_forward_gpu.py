@@ -341,3 +341,37 @@ def test_random_fuzz_all_paths(cuda):
     r = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_parity.py"), "20", "7"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "0 failures" in r.stdout
+
+
+def test_decode_adjacent_epilogue(cuda, photo):
+    """HWC uint8 -> AA resize -> (x/255 - mean)/std -> CHW fp16/bf16/fp32 in one kernel
+    (aa_resize_forward_ex: normalisation, half output and planar stores fused), on all three forward kernels."""
+    import interpolate_antialiasing_b200 as aa
+    from interpolate_antialiasing_b200 import capi
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    hwc = torch.from_numpy(np.stack([photo, photo[::-1].copy()])).to(cuda)        # [2, 438, 906, 3] uint8
+    xf = hwc.permute(0, 3, 1, 2).float().cpu().numpy()
+    for osize, mode in (((224, 224), "bilinear"), ((196, 320), "bicubic"), ((600, 1200), "bilinear"), ((438, 906), "bicubic")):
+        base = O.forward(xf, osize, {"bilinear": "linear", "bicubic": "cubic"}[mode], False)
+        want = (base / 255.0 - np.array(mean, np.float32)[None, :, None, None]) / np.array(std, np.float32)[None, :, None, None]
+        for dt, tol in ((torch.float32, 2e-5), (torch.float16, 2e-3), (torch.bfloat16, 2e-2)):
+            y = aa.decode_resize_normalize(hwc, osize, mean, std, mode, dt)
+            assert y.shape == (2, 3) + osize and y.dtype == dt and y.is_contiguous()
+            err = np.abs(y.float().cpu().numpy() - want)
+            assert err.max() <= tol * (1 + np.abs(want).max()), (osize, mode, dt, err.max())
+        # the same epilogue through the general (bit-exact accumulate) path and the forced streaming path
+        for flags in (capi.FLAG_FORCE_GENERAL, capi.FLAG_FORCE_STREAM):
+            out = torch.empty((2, 3) + osize, dtype=torch.float32, device=cuda)
+            try:
+                capi.resize_forward_ex(hwc.permute(0, 3, 1, 2), osize, mode, out, [1 / (255 * s) for s in std], [-m / s for m, s in zip(mean, std)], flags=flags)
+            except capi.AAError as e:
+                if "-2" in str(e) and flags == capi.FLAG_FORCE_STREAM:
+                    continue
+                raise
+            torch.cuda.synchronize()
+            assert np.abs(out.cpu().numpy() - want).max() <= 2e-5 * (1 + np.abs(want).max())
+    # planar output without normalisation, uint8 -> uint8 CHW
+    out = torch.empty((2, 3, 196, 320), dtype=torch.uint8, device=cuda)
+    capi.resize_forward_ex(hwc.permute(0, 3, 1, 2), (196, 320), "linear", out)
+    want8 = np.clip(O.forward(xf, (196, 320), "linear", False), 0, 255).astype(np.uint8)
+    assert np.abs(out.cpu().numpy().astype(np.int32) - want8.astype(np.int32)).max() <= 1
