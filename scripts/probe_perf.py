@@ -150,3 +150,19 @@ if "graph" in which:
     b4 = 64 * 3 * (128 * 128 + 512 * 512) * 4
     tb = burst_time(f4)
     print(f"cfg4 backward: python back-to-back {tb*1e3:7.2f} us/call ({b4/tb/1e6:7.1f} GB/s, {b4/tb/1e6/PEAK*100:5.1f}% of peak)")
+
+if "decode" in which:
+    import interpolate_antialiasing_b200 as aa
+    N = 128
+    hwc = torch.randint(0, 256, (N, 1080, 1920, 3), generator=g, device=dev, dtype=torch.uint8)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    b = N * 3 * (1080 * 1920 * 1 + 224 * 224 * 2)
+    med, best = timeit(lambda: aa.decode_resize_normalize(hwc, (224, 224), mean, std, "bilinear", torch.float16))
+    print(f"{'decode-adjacent: HWC u8 128x1080x1920x3 -> CHW fp16 224^2 (1 kernel)':58s} med {med*1e3:9.1f} us  {b/med/1e6:8.1f} GB/s  {b/med/1e6/PEAK*100:5.1f}% of peak", flush=True)
+    def unfused():
+        x = hwc.permute(0, 3, 1, 2).float()
+        y = torch.nn.functional.interpolate(x, size=(224, 224), mode="bilinear", antialias=True)
+        m = torch.tensor(mean, device=dev).view(1, 3, 1, 1); s = torch.tensor(std, device=dev).view(1, 3, 1, 1)
+        return ((y / 255.0 - m) / s).half().contiguous()
+    med2, _ = timeit(unfused, iters=5, warm=2)
+    print(f"{'same with torch ops (cast, F.interpolate AA, normalise, half)':58s} med {med2*1e3:9.1f} us  ({med2/med:.1f}x slower)", flush=True)
