@@ -1,0 +1,94 @@
+"""The host-buffer entry point (aa_resize_forward_host: H2D / kernel / D2H pipelined inside the C ABI),
+cache management and thread safety -- everything a non-torch host would exercise."""
+import ctypes
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import aa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(got, want, atol=1e-3, rtol=1e-5):
+    err = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    assert np.all(err <= atol + rtol * np.abs(want)), err.max()
+
+
+def test_host_entry_point(cuda):
+    from interpolate_antialiasing_b200 import capi
+    g = torch.Generator().manual_seed(3)
+    for shape, osize, mode, cl, dt in [((7, 3, 120, 200), (30, 50), "linear", False, torch.float32),     # uneven chunks (7 images / 3 streams)
+                                      ((5, 3, 96, 128), (48, 64), "cubic", True, torch.float32),
+                                      ((4, 3, 200, 320), (25, 40), "cubic", False, torch.uint8),
+                                      ((1, 1, 64, 64), (128, 128), "linear", False, torch.float32)]:
+        x = (torch.rand(shape, generator=g) * 255).to(dt)
+        if cl:
+            x = x.contiguous(memory_format=torch.channels_last)
+        want = O.forward(x.float().numpy(), osize, mode, False)
+        for pinned in (False, True):
+            xh = x.pin_memory() if pinned else x
+            fmt = torch.channels_last if cl else torch.contiguous_format
+            out = torch.empty((shape[0], shape[1]) + osize, dtype=torch.float32).contiguous(memory_format=fmt)
+            if pinned:
+                out = out.pin_memory()
+            capi.resize_forward_host(xh, out, mode, False, device=0)
+            _close(out.numpy(), want)
+        # fused uint8 output through the host path
+        out8 = torch.empty((shape[0], shape[1]) + osize, dtype=torch.uint8).contiguous(memory_format=fmt)
+        capi.resize_forward_host(x, out8, mode, False, flags=capi.FLAG_ROUND_NEAREST, device=0)
+        want8 = np.floor(np.clip(want, 0, 255) + 0.5)
+        assert np.abs(out8.numpy().astype(np.float64) - want8).max() <= 1
+    # empty batch: a no-op, not an error
+    capi.resize_forward_host(torch.empty((0, 3, 8, 8)), torch.empty((0, 3, 4, 4)), "linear", False, device=0)
+    # images that are not densely packed are refused with a status code
+    xb = torch.rand((4, 3, 16, 16))[::2]
+    with pytest.raises(capi.AAError):
+        capi.resize_forward_host(xb, torch.empty((2, 3, 8, 8)), "linear", False, device=0)
+
+
+def test_table_cache_clear_and_rebuild(cuda):
+    from interpolate_antialiasing_b200 import capi
+    x = torch.rand((1, 3, 50, 70), device=cuda) * 255
+    a = capi.resize_forward(x, (20, 30), "cubic")
+    n0 = capi.launch_count(reset=True)
+    b = capi.resize_forward(x, (20, 30), "cubic")
+    assert capi.launch_count(reset=True) == 1 and n0 >= 1          # warm cache: exactly one kernel launch per call
+    assert capi.lib().aa_clear_table_cache() == 0
+    c = capi.resize_forward(x, (20, 30), "cubic")
+    assert capi.launch_count(reset=True) >= 3                        # tables rebuilt (fwd + adjoint kernels per axis) + the op
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_concurrent_callers_on_their_own_streams(cuda):
+    """The library is stateless apart from the mutex-protected table / plan caches: threads on different
+    streams with different shapes must not disturb each other (SURVEY 8(b) Threading)."""
+    from interpolate_antialiasing_b200 import capi
+    capi.lib().aa_clear_table_cache()
+    errs = []
+
+    def work(seed):
+        try:
+            g = torch.Generator().manual_seed(seed)
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for k in range(12):
+                    h, w = 40 + 7 * seed + k, 64 + 5 * seed
+                    x = (torch.rand((2, 3, h, w), generator=g) * 255)
+                    osize = (h // 3 + 1, w // 2 + 1)
+                    y = capi.resize_forward(x.to(cuda, non_blocking=False), osize, "linear" if k % 2 else "cubic")
+                    s.synchronize()
+                    want = O.forward(x.numpy(), osize, "linear" if k % 2 else "cubic", False)
+                    _close(y.cpu().numpy(), want)
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
