@@ -149,7 +149,7 @@ def resize_forward_ex(x, output_size, filter, out, scale=None, bias=None, align_
     return out
 
 
-def resize_backward(grad_out, input_size, filter, align_corners=False, nonaa=False):
+def resize_backward(grad_out, input_size, filter, align_corners=False, nonaa=False, flags=FLAG_AUTO):
     import torch
     cl = grad_out.is_contiguous(memory_format=torch.channels_last) and not grad_out.is_contiguous()
     gin = torch.empty(tuple(input_size), dtype=grad_out.dtype, device=grad_out.device,
@@ -158,7 +158,7 @@ def resize_backward(grad_out, input_size, filter, align_corners=False, nonaa=Fal
     if nonaa:
         check(lib().aa_resize_backward_nonaa_bilinear(ctypes.byref(dg), ctypes.byref(di), int(align_corners), _stream(grad_out)))
     else:
-        check(lib().aa_resize_backward(ctypes.byref(dg), ctypes.byref(di), _filter(filter), int(align_corners), 0, _stream(grad_out)))
+        check(lib().aa_resize_backward(ctypes.byref(dg), ctypes.byref(di), _filter(filter), int(align_corners), flags, _stream(grad_out)))
     return gin
 
 

@@ -260,9 +260,15 @@ int aa_resize_backward(const aa_tensor_desc* gout, const aa_tensor_desc* gin, in
   if ((rc = get_axis_tables(gout->device, gin->h, gout->h, filter, align_corners, gout->dtype, stream, &th)) != AA_OK) return rc;
   if ((rc = get_axis_tables(gout->device, gin->w, gout->w, filter, align_corners, gout->dtype, stream, &tw)) != AA_OK) return rc;
   if (gout->dtype == AA_F32 && !(flags & AA_FLAG_FORCE_GENERAL)) {
-    rc = launch_tile(gout->data, gout->dtype, lo, gin->data, li, adj_axis(th.get()), adj_axis(tw.get()), th->kt_max,
-                     tw->kt_max, OutEpi(), stream);
-    if (rc != AA_ERR_UNSUPPORTED) return rc;
+    // few adjoint taps (the forward was a downsampling): write-bound tile kernel; many taps (the forward was
+    // an upsampling): the backward is the input-bound direction -> streaming kernel with the roles swapped
+    if (!(flags & AA_FLAG_FORCE_STREAM)) {
+      rc = launch_tile(gout->data, gout->dtype, lo, gin->data, li, adj_axis(th.get()), adj_axis(tw.get()), th->kt_max,
+                       tw->kt_max, OutEpi(), stream);
+      if (rc != AA_ERR_UNSUPPORTED) return rc;
+    }
+    rc = launch_stream_adjoint(gout->data, lo, gin->data, li, th.get(), tw.get(), stream);
+    if (rc != AA_ERR_UNSUPPORTED || (flags & AA_FLAG_FORCE_STREAM)) return rc;
   }
   return launch_general(gout->data, gout->dtype, lo, gin->data, gin->dtype, li, adj_axis(th.get()), adj_axis(tw.get()),
                         /*exact=*/false, OutEpi(), stream);

@@ -66,6 +66,10 @@ struct AxisTables {
   int slot_RS = 0;           // record stride in 32-bit words = roundup4(A+1)
   float* slot = nullptr;     // [in][RS]: wT[y][0..A) ordered by age (k-th oldest open output row), then
                              //           (first_flush_o | nflush<<24)
+  // the same records for the ADJOINT direction (grad_out rows streamed, grad_in rows produced): per
+  // forward-output row o, the forward weights w[o][0..A) belong to the open grad_in rows xmin[o]+k
+  int slot_adj_A = 0, slot_adj_RS = 0;
+  float* slot_adj = nullptr;  // [out][RS]
   // host mirrors of the integer tables (for launch planning)
   std::vector<int32_t> h_xmin, h_xsize, h_omin, h_osize;
   ~AxisTables();
@@ -76,6 +80,7 @@ int get_axis_tables(int device, int64_t in, int64_t out, int filter, int align, 
                     cudaStream_t stream, std::shared_ptr<AxisTables>* result);
 // Makes sure t->slot exists for `A` accumulators (A in 3..6); launches one tiny kernel on first use.
 int ensure_slot_tables(AxisTables* t, int A, cudaStream_t stream);
+int ensure_slot_tables_adj(AxisTables* t, int A, cudaStream_t stream);
 int clear_table_cache();
 // Host-only K computation (no device), same arithmetic as the table kernel.
 int host_interp_size(int64_t in, int64_t out, int filter, int align, int dtype);
@@ -173,6 +178,11 @@ int launch_tile(const void* in, int in_dtype, const Layout& lin, void* out, cons
 int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout,
                   AxisTables* th, AxisTables* tw, int64_t H, int64_t W, int64_t oH, int64_t oW,
                   uint32_t flags, OutEpi epi, cudaStream_t stream);
+
+// The adjoint (grad_in = Wh^T g Ww) on the same streaming kernel: used when the FORWARD was an upsampling,
+// i.e. the backward is the many-taps, input-bound direction.  AA_ERR_UNSUPPORTED when not eligible.
+int launch_stream_adjoint(const void* gout, const Layout& lo, void* gin, const Layout& li, AxisTables* th, AxisTables* tw,
+                          cudaStream_t stream);
 
 int launch_backward_nonaa(const void* gout, void* gin, int dtype, const Layout& lout, const Layout& lin,
                           int64_t oH, int64_t oW, int64_t H, int64_t W, int align, cudaStream_t stream);

@@ -181,20 +181,20 @@ struct Cfg {
 };
 
 template <int A, int VEC, typename in_t, int NT_ = 256, bool GEN = false>
-int launch_cfg(SParams& P, const AxisTables* th, const AxisTables* tw, int device, cudaStream_t stream) {
+int launch_cfg(SParams& P, const StreamTables& T, int device, cudaStream_t stream) {
   using C = Cfg<A, VEC, in_t, NT_>;
   if constexpr (!GEN && NT_ == 256 && (VEC == 4 || (VEC == 8 && sizeof(in_t) == 1))) {
     // decode-adjacent epilogue (normalise / half / planar): separate instantiations of the common shapes
-    if (P.epi.generic()) return launch_cfg<A, VEC, in_t, NT_, true>(P, th, tw, device, stream);
+    if (P.epi.generic()) return launch_cfg<A, VEC, in_t, NT_, true>(P, T, device, stream);
   } else if constexpr (!GEN) {
     if (P.epi.generic()) return fail(AA_ERR_UNSUPPORTED, "stream: generic epilogue not instantiated for this shape");
   }
   auto kern = aa_stream_kernel<A, VEC, in_t, C::NT, C::U, C::MINB, GEN>;
-  const PlanKey key{th, tw, P.Ci, (GEN ? (1 << 28) : 0) | (NT_ << 16) | (A << 8) | (VEC << 2) | (int)sizeof(in_t) % 4};
+  const PlanKey key{T.key_h, T.key_w, P.Ci, (T.dir << 29) | (GEN ? (1 << 28) : 0) | (NT_ << 16) | (A << 8) | (VEC << 2) | (int)sizeof(in_t) % 4};
   Plan pl;
   if (!plan_lookup(key, &pl)) {
     P.in_pitch = 0;
-    int rc = plan_stream(P, th, tw, C::NT * VEC, VEC, VEC, C::U, C::TG);
+    int rc = plan_stream(P, T, C::NT * VEC, VEC, VEC, C::U, C::TG);
     if (rc != AA_OK) return rc;
     const size_t smem_ = sizeof(float) * (size_t)P.vr * P.vw + strip_table_bytes(P);
     if (smem_ > 200 * 1024) return fail(AA_ERR_UNSUPPORTED, "stream: shared memory plan too large");
@@ -221,16 +221,16 @@ int launch_cfg(SParams& P, const AxisTables* th, const AxisTables* tw, int devic
 }
 
 template <int A>
-int launch_A(SParams& P, int in_dtype, int vec, const AxisTables* th, const AxisTables* tw, int device, cudaStream_t stream) {
+int launch_A(SParams& P, int in_dtype, int vec, const StreamTables& T, int device, cudaStream_t stream) {
   if (in_dtype == AA_F32) {
     // narrow rows: a 128-thread CTA covers the whole row, so no lanes idle through the vertical pass
-    if (vec == 4 && tw->in * P.Ci <= 128 * 4) return launch_cfg<A, 4, float, 128>(P, th, tw, device, stream);
-    if (vec == 4) return launch_cfg<A, 4, float>(P, th, tw, device, stream);
-    if (vec == 2) return launch_cfg<A, 2, float>(P, th, tw, device, stream);
-    return launch_cfg<A, 1, float>(P, th, tw, device, stream);
+    if (vec == 4 && T.n_in_w * P.Ci <= 128 * 4) return launch_cfg<A, 4, float, 128>(P, T, device, stream);
+    if (vec == 4) return launch_cfg<A, 4, float>(P, T, device, stream);
+    if (vec == 2) return launch_cfg<A, 2, float>(P, T, device, stream);
+    return launch_cfg<A, 1, float>(P, T, device, stream);
   }
-  if (vec == 8) return launch_cfg<A, 8, uint8_t>(P, th, tw, device, stream);
-  return launch_cfg<A, 4, uint8_t>(P, th, tw, device, stream);
+  if (vec == 8) return launch_cfg<A, 8, uint8_t>(P, T, device, stream);
+  return launch_cfg<A, 4, uint8_t>(P, T, device, stream);
 }
 
 }  // namespace
@@ -257,14 +257,9 @@ void plan_clear() {
 }
 }  // namespace stream_detail
 
-int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout,
-                  AxisTables* th, AxisTables* tw, int64_t H, int64_t W, int64_t oH, int64_t oW,
-                  uint32_t flags, OutEpi epi, cudaStream_t stream) {
-  if (in_dtype != AA_F32 && in_dtype != AA_U8) return fail(AA_ERR_UNSUPPORTED, "stream: input must be f32 or u8");
-  if (th->dtype != AA_F32 || tw->dtype != AA_F32) return fail(AA_ERR_UNSUPPORTED, "stream: f32 tables only");
-  if (th->kt_max > kMaxA) return fail(AA_ERR_UNSUPPORTED, "stream: too many output rows per input row (upsampling in H)");
-  if (oH >= (1 << 24) || W * lin.Ci >= (1ll << 30) || tw->K >= (1 << 16) || lin.Ci > 2047) return fail(AA_ERR_UNSUPPORTED, "stream: size limits");
-  // widest vector the addresses allow: base pointer, plane strides and row stride must all be aligned
+namespace {
+// widest vector the addresses allow: base pointer, plane strides and row stride must all be aligned
+int pick_vec(const void* in, int in_dtype, const Layout& lin) {
   const int es = in_dtype == AA_F32 ? 4 : 1;
   auto aligned = [&](int vec) {
     const int64_t bytes = (int64_t)vec * es;
@@ -272,9 +267,30 @@ int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, co
     if ((lin.stride_h % vec) || (lin.stride_n % vec) || (lin.Cp > 1 && lin.stride_p % vec)) return false;
     return true;
   };
-  int vec = 0;
-  if (in_dtype == AA_F32) { for (int v : {4, 2, 1}) if (aligned(v)) { vec = v; break; } }
-  else { for (int v : {8, 4}) if (aligned(v)) { vec = v; break; } }
+  if (in_dtype == AA_F32) { for (int v : {4, 2, 1}) if (aligned(v)) return v; }
+  else { for (int v : {8, 4}) if (aligned(v)) return v; }
+  return 0;
+}
+int dispatch_A(SParams& P, int A, int in_dtype, int vec, const StreamTables& T, int device, uint32_t flags, cudaStream_t stream) {
+  if (flags & AA_FLAG_STREAM_TMA) return launch_stream_tma(P, A, in_dtype, T, device, stream);
+  switch (A) {
+    case 3: return launch_A<3>(P, in_dtype, vec, T, device, stream);
+    case 4: return launch_A<4>(P, in_dtype, vec, T, device, stream);
+    case 5: return launch_A<5>(P, in_dtype, vec, T, device, stream);
+    case 6: return launch_A<6>(P, in_dtype, vec, T, device, stream);
+  }
+  return fail(AA_ERR_UNSUPPORTED, "stream: unsupported accumulator count");
+}
+}  // namespace
+
+int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout,
+                  AxisTables* th, AxisTables* tw, int64_t H, int64_t W, int64_t oH, int64_t oW,
+                  uint32_t flags, OutEpi epi, cudaStream_t stream) {
+  if (in_dtype != AA_F32 && in_dtype != AA_U8) return fail(AA_ERR_UNSUPPORTED, "stream: input must be f32 or u8");
+  if (th->dtype != AA_F32 || tw->dtype != AA_F32) return fail(AA_ERR_UNSUPPORTED, "stream: f32 tables only");
+  if (th->kt_max > kMaxA) return fail(AA_ERR_UNSUPPORTED, "stream: too many output rows per input row (upsampling in H)");
+  if (oH >= (1 << 24) || W * lin.Ci >= (1ll << 30) || tw->K >= (1 << 16) || lin.Ci > 2047) return fail(AA_ERR_UNSUPPORTED, "stream: size limits");
+  const int vec = pick_vec(in, in_dtype, lin);
   if (!vec) return fail(AA_ERR_UNSUPPORTED, "stream: input rows are not sufficiently aligned");
   const int A = th->kt_max <= 3 ? 3 : th->kt_max;
   int rc = ensure_slot_tables(th, A, stream);
@@ -286,14 +302,34 @@ int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, co
   P.slot_h = th->slot; P.RS = th->slot_RS;
   P.xmin_h = th->xmin; P.xsize_h = th->xsize;
   P.xmin_w = tw->xmin; P.xsize_w = tw->xsize; P.w_w = (const float*)tw->w; P.Kw = tw->K;
-  if (flags & AA_FLAG_STREAM_TMA) return launch_stream_tma(P, A, in_dtype, th, tw, th->device, stream);
-  switch (A) {
-    case 3: return launch_A<3>(P, in_dtype, vec, th, tw, th->device, stream);
-    case 4: return launch_A<4>(P, in_dtype, vec, th, tw, th->device, stream);
-    case 5: return launch_A<5>(P, in_dtype, vec, th, tw, th->device, stream);
-    case 6: return launch_A<6>(P, in_dtype, vec, th, tw, th->device, stream);
-  }
-  return fail(AA_ERR_UNSUPPORTED, "stream: unsupported accumulator count");
+  const StreamTables T{th, tw, 0, th->h_xmin.data(), th->h_xsize.data(), oH, tw->h_xmin.data(), tw->h_xsize.data(), W, oW};
+  return dispatch_A(P, A, in_dtype, vec, T, th->device, flags, stream);
+}
+
+int launch_stream_adjoint(const void* gout, const Layout& lo, void* gin, const Layout& li, AxisTables* th, AxisTables* tw,
+                          cudaStream_t stream) {
+  // grad_out [.., oH, oW] is streamed, grad_in [.., H, W] is produced: the roles of the two table sets swap.
+  if (th->dtype != AA_F32 || tw->dtype != AA_F32) return fail(AA_ERR_UNSUPPORTED, "stream: f32 tables only");
+  const int64_t H = th->in, oH = th->out, W = tw->in, oW = tw->out;
+  if (th->xsize_max > kMaxA) return fail(AA_ERR_UNSUPPORTED, "stream/adjoint: too many grad_in rows per grad_out row");
+  if (H >= (1 << 24) || oW * lo.Ci >= (1ll << 30) || tw->KT >= (1 << 16) || lo.Ci > 2047) return fail(AA_ERR_UNSUPPORTED, "stream/adjoint: size limits");
+  // every grad_in row / column must be covered by at least one grad_out row / column (else it is never written)
+  for (int64_t y = 0; y < H; y++) if (th->h_osize[y] < 1) return fail(AA_ERR_UNSUPPORTED, "stream/adjoint: uncovered rows");
+  for (int64_t x = 0; x < W; x++) if (tw->h_osize[x] < 1) return fail(AA_ERR_UNSUPPORTED, "stream/adjoint: uncovered columns");
+  const int vec = pick_vec(gout, AA_F32, lo);
+  if (!vec) return fail(AA_ERR_UNSUPPORTED, "stream/adjoint: rows are not sufficiently aligned");
+  const int A = th->xsize_max <= 3 ? 3 : th->xsize_max;
+  int rc = ensure_slot_tables_adj(th, A, stream);
+  if (rc != AA_OK) return rc;
+
+  SParams P;
+  P.in = gout; P.out = gin; P.epi = OutEpi(); P.lin = lo; P.lout = li; P.Ci = lo.Ci;
+  P.H = oH; P.oH = H; P.oW = W;
+  P.slot_h = th->slot_adj; P.RS = th->slot_adj_RS;
+  P.xmin_h = th->omin; P.xsize_h = th->osize;
+  P.xmin_w = tw->omin; P.xsize_w = tw->osize; P.w_w = (const float*)tw->wT; P.Kw = tw->KT;
+  const StreamTables T{th, tw, 1, th->h_omin.data(), th->h_osize.data(), H, tw->h_omin.data(), tw->h_osize.data(), oW, W};
+  return dispatch_A(P, A, AA_F32, vec, T, th->device, 0u, stream);
 }
 
 }  // namespace aa

@@ -295,11 +295,22 @@ inline size_t strip_table_bytes(const SParams& P) {
   return (size_t)P.wtab_bytes + 16 + items * sizeof(int4);
 }
 
+// Host-side view of the tables for one direction of the banded separable apply (forward, or adjoint when
+// the backward is the downsampling-shaped direction).  "Output rows" are the rows the kernel produces.
+struct StreamTables {
+  const void *key_h, *key_w;              // identity for the plan cache
+  int dir;                                // 0 forward, 1 adjoint
+  const int32_t *hh_start, *hh_size;      // host: per output row, first input row and window length
+  int64_t n_out_h;
+  const int32_t *hw_start, *hw_size;      // host: per output column, first input column and window length
+  int64_t n_in_w, n_out_w;
+};
+
 // Strip / row-buffer plan shared by both variants (exact, from the host mirrors of the tables).
 //   cap   flat elements one strip may span (threads * VEC)
 //   aln   alignment of a strip's first element (VEC, or 16 bytes' worth for the TMA variant)
 //   U     input rows processed between two checks of the row buffer
-inline int plan_stream(SParams& P, const AxisTables* th, const AxisTables* tw, int cap, int aln, int vec, int U, int tg) {
+inline int plan_stream(SParams& P, const StreamTables& T, int cap, int aln, int vec, int U, int tg) {
   const int64_t oW = P.oW;
   const int Ci = P.Ci;
   int n_strips = 1, strip_ox = (int)oW;
@@ -311,8 +322,8 @@ inline int plan_stream(SParams& P, const AxisTables* th, const AxisTables* tw, i
     max_extent = 0;
     for (int64_t a = 0; ok && a < oW; a += strip_ox) {
       const int64_t b = std::min<int64_t>(oW, a + strip_ox) - 1;
-      const int64_t f0 = ((int64_t)tw->h_xmin[a] * Ci) & ~(int64_t)(aln - 1);
-      const int64_t f1 = ((int64_t)tw->h_xmin[b] + tw->h_xsize[b]) * Ci;
+      const int64_t f0 = ((int64_t)T.hw_start[a] * Ci) & ~(int64_t)(aln - 1);
+      const int64_t f1 = ((int64_t)T.hw_start[b] + T.hw_size[b]) * Ci;
       if (f1 - f0 > cap) ok = false;
       max_extent = std::max(max_extent, f1 - f0);
     }
@@ -329,15 +340,15 @@ inline int plan_stream(SParams& P, const AxisTables* th, const AxisTables* tw, i
     const int64_t oH = P.oH;
     int64_t lo = 0;
     for (int64_t o = 0; o < oH; o++) {  // ends are non-decreasing
-      const int64_t e = (int64_t)th->h_xmin[o] + th->h_xsize[o];
-      while ((int64_t)th->h_xmin[lo] + th->h_xsize[lo] <= e - U) lo++;
+      const int64_t e = (int64_t)T.hh_start[o] + T.hh_size[o];
+      while ((int64_t)T.hh_start[lo] + T.hh_size[lo] <= e - U) lo++;
       fmax = std::max<int>(fmax, (int)(o - lo + 1));
     }
   }
   int shift = 0;
   for (int64_t a = 0; a < oW; a += strip_ox)
     for (int64_t o = a; o + 1 < std::min<int64_t>(oW, a + strip_ox); o += 2)
-      shift = std::max<int>(shift, tw->h_xmin[o + 1] - tw->h_xmin[o]);
+      shift = std::max<int>(shift, T.hw_start[o + 1] - T.hw_start[o]);
   P.kp = P.Kw + shift;
   P.pairs = (int64_t)strip_ox * Ci >= 256 ? 1 : 0;  // enough independent items per row group to halve them
   P.wtab_bytes = P.pairs ? (int)((size_t)((strip_ox + 1) / 2) * P.kp * sizeof(float2)) : (int)((size_t)strip_ox * P.Kw * sizeof(float));
@@ -384,7 +395,7 @@ inline Plan plan_from(const SParams& P, size_t smem, int max_grid) {
 }  // namespace stream_detail
 
 // TMA variant launcher (aa_stream_tma.cu); AA_ERR_UNSUPPORTED when rows are not 16-byte aligned.
-int launch_stream_tma(stream_detail::SParams& P, int A, int in_dtype, const AxisTables* th, const AxisTables* tw, int device,
+int launch_stream_tma(stream_detail::SParams& P, int A, int in_dtype, const stream_detail::StreamTables& T, int device,
                       cudaStream_t stream);
 
 }  // namespace aa

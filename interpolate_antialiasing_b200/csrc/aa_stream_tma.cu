@@ -239,15 +239,15 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
 }
 
 template <int A, int VEC, typename in_t>
-int launch_tma_cfg(SParams& P, const AxisTables* th, const AxisTables* tw, int device, cudaStream_t stream) {
+int launch_tma_cfg(SParams& P, const StreamTables& T, int device, cudaStream_t stream) {
   constexpr int R = 4, STAGES = 4;
   constexpr int MINB = 2;
   constexpr int ES = (int)sizeof(in_t);
   auto kern = aa_stream_tma_kernel<A, VEC, in_t, R, STAGES, MINB>;
-  const PlanKey key{th, tw, P.Ci, 0x10000 | (A << 8) | (VEC << 2) | ES % 4};
+  const PlanKey key{T.key_h, T.key_w, P.Ci, (T.dir << 29) | 0x10000 | (A << 8) | (VEC << 2) | ES % 4};
   Plan pl;
   if (!plan_lookup(key, &pl)) {
-    int rc = plan_stream(P, th, tw, NTC * VEC, 16 / ES, VEC, R, 4);
+    int rc = plan_stream(P, T, NTC * VEC, 16 / ES, VEC, R, 4);
     if (rc != AA_OK) return rc;
     P.in_pitch = (P.vw * ES + 15) & ~15;
     const size_t smem_ = (size_t)STAGES * R * P.in_pitch + sizeof(float) * (size_t)P.vr * P.vw + strip_table_bytes(P) + 8 + 16 * STAGES;
@@ -269,14 +269,14 @@ int launch_tma_cfg(SParams& P, const AxisTables* th, const AxisTables* tw, int d
 }
 
 template <int A>
-int launch_tma_A(SParams& P, int in_dtype, const AxisTables* th, const AxisTables* tw, int device, cudaStream_t stream) {
-  if (in_dtype == AA_F32) return launch_tma_cfg<A, 4, float>(P, th, tw, device, stream);
-  return launch_tma_cfg<A, 8, uint8_t>(P, th, tw, device, stream);
+int launch_tma_A(SParams& P, int in_dtype, const StreamTables& T, int device, cudaStream_t stream) {
+  if (in_dtype == AA_F32) return launch_tma_cfg<A, 4, float>(P, T, device, stream);
+  return launch_tma_cfg<A, 8, uint8_t>(P, T, device, stream);
 }
 
 }  // namespace
 
-int launch_stream_tma(SParams& P, int A, int in_dtype, const AxisTables* th, const AxisTables* tw, int device, cudaStream_t stream) {
+int launch_stream_tma(SParams& P, int A, int in_dtype, const StreamTables& T, int device, cudaStream_t stream) {
   if (P.epi.generic()) return fail(AA_ERR_UNSUPPORTED, "stream/tma: generic epilogue not instantiated");
   // cp.async.bulk needs 16-byte aligned global addresses and sizes: base, plane and row strides
   const int es = in_dtype == AA_F32 ? 4 : 1;
@@ -284,10 +284,10 @@ int launch_stream_tma(SParams& P, int A, int in_dtype, const AxisTables* th, con
   if (((uintptr_t)P.in) % 16 || (P.lin.stride_h % al) || (P.lin.stride_n % al) || (P.lin.Cp > 1 && P.lin.stride_p % al))
     return fail(AA_ERR_UNSUPPORTED, "stream/tma: input rows are not 16-byte aligned");
   switch (A) {
-    case 3: return launch_tma_A<3>(P, in_dtype, th, tw, device, stream);
-    case 4: return launch_tma_A<4>(P, in_dtype, th, tw, device, stream);
-    case 5: return launch_tma_A<5>(P, in_dtype, th, tw, device, stream);
-    case 6: return launch_tma_A<6>(P, in_dtype, th, tw, device, stream);
+    case 3: return launch_tma_A<3>(P, in_dtype, T, device, stream);
+    case 4: return launch_tma_A<4>(P, in_dtype, T, device, stream);
+    case 5: return launch_tma_A<5>(P, in_dtype, T, device, stream);
+    case 6: return launch_tma_A<6>(P, in_dtype, T, device, stream);
   }
   return fail(AA_ERR_UNSUPPORTED, "stream/tma: unsupported accumulator count");
 }

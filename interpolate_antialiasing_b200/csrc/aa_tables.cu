@@ -241,6 +241,24 @@ __global__ void aa_tables_slots(int64_t in, int A, int RS, int KT, const int32_t
   rec[A] = __int_as_float(o0 | (nflush << 24));
 }
 
+// Adjoint direction: one thread per forward-output index o (= a streamed grad_out row).  The open
+// grad_in rows at o are [xmin[o], xmin[o]+xsize[o]) with the forward weights; the ones that no later o
+// covers (y < xmin[o+1]) finish here.
+__global__ void aa_tables_slots_adj(int64_t out, int A, int RS, int K, const int32_t* __restrict__ xmin,
+                                    const int32_t* __restrict__ xsize, const float* __restrict__ w,
+                                    float* __restrict__ slot) {
+  int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= out) return;
+  float* rec = slot + o * RS;
+  for (int a = 0; a < RS; a++) rec[a] = 0.0f;
+  const int x0 = xmin[o], n = xsize[o];
+  for (int k = 0; k < n && k < A; k++) rec[k] = w[o * K + k];
+  const int end = x0 + n;
+  const int nxt = (o + 1 < out) ? xmin[o + 1] : end;
+  const int nflush = (nxt < end ? nxt : end) - x0;
+  rec[A] = __int_as_float(x0 | (nflush << 24));
+}
+
 // ------------------------------------------------------------------------------------------------
 // cache
 // ------------------------------------------------------------------------------------------------
@@ -251,6 +269,7 @@ AxisTables::~AxisTables() {
     cudaSetDevice(device);
     if (block) cudaFree(block);
     if (slot) cudaFree(slot);
+    if (slot_adj) cudaFree(slot_adj);
     cudaSetDevice(cur);
   }
 }
@@ -387,6 +406,24 @@ int ensure_slot_tables(AxisTables* t, int A, cudaStream_t stream) {
 }
 
 namespace stream_detail { void plan_clear(); }
+
+int ensure_slot_tables_adj(AxisTables* t, int A, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (t->dtype != AA_F32) return fail(AA_ERR_UNSUPPORTED, "slot tables are float only");
+  if (t->slot_adj && t->slot_adj_A == A) return AA_OK;
+  if (t->slot_adj) return fail(AA_ERR_INVALID, "internal: adjoint slot tables requested with two different A");
+  if (t->in >= (1 << 24)) return fail(AA_ERR_UNSUPPORTED, "streaming path needs in < 2^24");
+  const int RS = (A + 1 + 3) / 4 * 4;
+  AA_CUDA_TRY(cudaMalloc(&t->slot_adj, sizeof(float) * (size_t)t->out * RS));
+  const int NT = 128;
+  aa_tables_slots_adj<<<(unsigned)((t->out + NT - 1) / NT), NT, 0, stream>>>(t->out, A, RS, t->K, t->xmin, t->xsize,
+                                                                             (const float*)t->w, t->slot_adj);
+  AA_LAUNCH_CHECK("aa_tables_slots_adj");
+  AA_CUDA_TRY(cudaStreamSynchronize(stream));  // first use only
+  t->slot_adj_A = A;
+  t->slot_adj_RS = RS;
+  return AA_OK;
+}
 
 int clear_table_cache() {
   stream_detail::plan_clear();

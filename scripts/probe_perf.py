@@ -166,3 +166,18 @@ if "decode" in which:
         return ((y / 255.0 - m) / s).half().contiguous()
     med2, _ = timeit(unfused, iters=5, warm=2)
     print(f"{'same with torch ops (cast, F.interpolate AA, normalise, half)':58s} med {med2*1e3:9.1f} us  ({med2/med:.1f}x slower)", flush=True)
+
+if "bwd" in which:
+    for mode in ("linear", "cubic"):
+        for (ih, oh) in ((512, 128), (1024, 512), (1024, 768), (512, 512), (512, 1024), (256, 1024)):
+            C = 3
+            per_img = C * (ih * ih + oh * oh) * 4
+            N = max(1, int(4.0e8 // per_img))
+            go = torch.rand((N, C, oh, oh), generator=g, device=dev)
+            try:
+                capi.resize_backward(go, (N, C, ih, ih), mode)
+                med, best = timeit(lambda: capi.resize_backward(go, (N, C, ih, ih), mode), iters=5, warm=2)
+                gbs = N * per_img / med / 1e6
+                print(f"bwd {mode:6s} grad_out {oh}^2 -> grad_in {ih}^2 N={N:3d} {med*1e3:9.1f} us {gbs:8.1f} GB/s {gbs/PEAK*100:5.1f}%", flush=True)
+            except capi.AAError as e:
+                print("bwd ERROR", mode, ih, oh, e)

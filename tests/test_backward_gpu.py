@@ -148,3 +148,33 @@ def test_custom_op_compile_and_autograd(cuda):
         return torch.ops.aa_b200.resize(t * 2.0, [16, 24], "bicubic", False).sum()
     fc = torch.compile(f, fullgraph=True, backend="aot_eager")
     assert torch.allclose(fc(x.detach()), f(x.detach()))
+
+
+def test_backward_of_upsampling_on_streaming_kernel(cuda):
+    """When the forward was an upsampling, the backward is the many-taps, input-bound direction: it runs on
+    the streaming kernel with the roles of the tables swapped (forced here; AUTO picks it when the tile kernel
+    declines).  Also mixed directions and both layouts."""
+    from interpolate_antialiasing_b200 import capi
+    g = torch.Generator().manual_seed(21)
+    cases = [((2, 3, 32, 48), (128, 192)), ((1, 4, 40, 64), (100, 200)), ((2, 1, 64, 64), (256, 96)),
+             ((1, 3, 128, 128), (512, 512)), ((3, 3, 37, 53), (75, 211)), ((1, 3, 64, 64), (64, 64))]
+    ran = 0
+    for shp, osz in cases:
+        for mode in ("linear", "cubic", "nearest"):
+            for cl in (False, True):
+                go = torch.rand(shp[:2] + osz, generator=g)
+                want = O.backward_adjoint(go.numpy(), shp, mode, False)
+                gc = go.to(cuda)
+                if cl:
+                    gc = gc.contiguous(memory_format=torch.channels_last)
+                for flags in (capi.FLAG_AUTO, capi.FLAG_FORCE_STREAM):
+                    try:
+                        got = capi.resize_backward(gc, shp, mode, False, flags=flags)
+                    except capi.AAError as e:
+                        if "-2" in str(e) and flags == capi.FLAG_FORCE_STREAM:
+                            continue
+                        raise
+                    torch.cuda.synchronize()
+                    ran += flags == capi.FLAG_FORCE_STREAM
+                    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-4)
+    assert ran >= 12
