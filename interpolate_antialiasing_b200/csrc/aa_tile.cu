@@ -42,6 +42,7 @@ struct TParams {
   int pr;    // rows of patch / T buffers (max input rows per tile + KH - 1)
   int pcp;   // patch pitch in floats (max input flat cols per tile + (KW-1)*Ci, padded)
   int vec_store;  // rows of out are 16-byte aligned -> float4 stores
+  int64_t plane0;  // first plane of this launch (planes are launched in slabs of <= 65535)
 };
 
 template <typename in_t> __device__ __forceinline__ float ldf(const in_t* p) { return (float)__ldg(p); }
@@ -55,13 +56,14 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
   float* patch = reinterpret_cast<float*>(hrec + TY * HR);             // [pr][pcp]
   const int tid = threadIdx.x;
   const int tx = tid % TXV, ty = tid / TXV;
-  int b = blockIdx.x;
-  const int tile_x = b % P.tiles_x; b /= P.tiles_x;
-  const int tile_y = b % P.tiles_y; b /= P.tiles_y;
-  const int64_t plane = b;
+  // grid = (tiles_x, tiles_y, planes): no index decode; in and out share Cp (same memory format family)
+  const int tile_x = blockIdx.x, tile_y = blockIdx.y;
+  const int64_t plane = (int64_t)blockIdx.z + P.plane0;
   const int Ci = P.Ci;
-  const in_t* ip = (const in_t*)P.in + (plane / P.lin.Cp) * P.lin.stride_n + (plane % P.lin.Cp) * P.lin.stride_p;
-  const int64_t op = (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p;  // element offset
+  int64_t pn = plane, pp = 0;
+  if (P.lin.Cp > 1) { pn = plane / P.lin.Cp; pp = plane - pn * P.lin.Cp; }
+  const in_t* ip = (const in_t*)P.in + pn * P.lin.stride_n + pp * P.lin.stride_p;
+  const int64_t op = pn * P.lout.stride_n + pp * P.lout.stride_p;  // element offset
 
   // tile extents (starts and ends are non-decreasing in the output index)
   const int oy0 = tile_y * TY, oy1 = min(P.out_h, oy0 + TY);
@@ -150,16 +152,17 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
   __syncthreads();
   // ---- stage 1: horizontal pass -> Ts
   {
-    const float* src = patch + soff;
+    const float* src[KW];  // one pointer per tap: the loop body is then LDS + FFMA only
+#pragma unroll
+    for (int k = 0; k < KW; k++) src[k] = patch + soff + k * Ci;
     float* dst = Ts + tid;
+    const int pcp = P.pcp;
 #pragma unroll 4
     for (int r = 0; r < prt; r++) {
       float a = 0.f;
 #pragma unroll
-      for (int k = 0; k < KW; k++) a = fmaf(src[k * Ci], w[k], a);
-      *dst = a;
-      src += P.pcp;
-      dst += TXF;
+      for (int k = 0; k < KW; k++) a = fmaf(src[k][r * pcp], w[k], a);
+      dst[r * TXF] = a;
     }
   }
   __syncthreads();
@@ -225,13 +228,16 @@ int launch_ty(TParams& P, int64_t planes, const BandedAxis& ah, size_t smem_limi
   P.tiles_y = (P.out_h + TY - 1) / TY;
   const size_t smem = sizeof(float) * ((size_t)P.pr * TXF + (size_t)TY * HR * 4 + (size_t)P.pr * P.pcp);
   if (smem > smem_limit) return fail(AA_ERR_UNSUPPORTED, "tile: input patch too large; use the streaming/general path");
-  const int64_t nblocks = (int64_t)P.tiles_x * P.tiles_y * planes;
-  if (nblocks <= 0) return AA_OK;
-  if (nblocks >= (1ll << 31)) return fail(AA_ERR_UNSUPPORTED, "tile: too many tiles");
+  if (planes <= 0) return AA_OK;
+  if (P.tiles_y > 65535) return fail(AA_ERR_UNSUPPORTED, "tile: too many row tiles");
   auto kern = aa_tile_kernel<KH, KW, TY, GEN, in_t>;
   if (smem > 48 * 1024) AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)nblocks, NT, smem, stream>>>(P);
-  AA_LAUNCH_CHECK("aa_tile_kernel");
+  for (int64_t p0 = 0; p0 < planes; p0 += 65535) {
+    P.plane0 = p0;
+    const dim3 grid((unsigned)P.tiles_x, (unsigned)P.tiles_y, (unsigned)std::min<int64_t>(65535, planes - p0));
+    kern<<<grid, NT, smem, stream>>>(P);
+    AA_LAUNCH_CHECK("aa_tile_kernel");
+  }
   return AA_OK;
 }
 
