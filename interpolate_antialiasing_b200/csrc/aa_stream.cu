@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
     const float4* rp = reinterpret_cast<const float4*>(P.slot_h) + yA * RS4;
     const int64_t op = (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p;  // element offset of the plane
     float* vdst = Vs + VEC * t;
+    float* vptr = vdst;          // where the next finished row goes
+    const bool vstore = valid;   // (kept in a predicate-friendly local)
 
     float acc[A][VEC];
 #pragma unroll
@@ -114,12 +116,15 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
       vfma<A, VEC>(acc, v, rw);
       const int packed = __float_as_int(rw[A]);
       if (packed >> 24) {
-        const int nfl = packed >> 24;
+        int nfl = packed >> 24;
         int o = packed & 0xffffff;
+        // lean retire loop (it runs once per scale_h input rows: at small scales it rivals the FMAs):
+        // a running shared-memory pointer instead of cnt*pitch, the strip predicate kept in `vstore`
 #pragma unroll 1
-        for (int k = 0; k < nfl; k++, o++) {
+        do {
           if (o >= oyA && o < oyB) {
-            if (valid) store_vec<VEC>(vdst + (size_t)cnt * vw, acc[0]);
+            if (vstore) store_vec<VEC>(vptr, acc[0]);
+            vptr += VW;
             cnt++;
           }
 #pragma unroll
@@ -128,7 +133,8 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
             for (int e = 0; e < VEC; e++) acc[a][e] = acc[a + 1][e];
 #pragma unroll
           for (int e = 0; e < VEC; e++) acc[A - 1][e] = 0.f;
-        }
+          o++;
+        } while (--nfl);
       }
     };
     // horizontal filter over the buffered rows [gbase, gbase+cnt)
@@ -138,6 +144,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
       __syncthreads();
       gbase += cnt;
       cnt = 0;
+      vptr = vdst;
     };
 
     int64_t y = yA;
