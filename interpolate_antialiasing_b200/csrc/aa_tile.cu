@@ -28,6 +28,25 @@ constexpr int TXF = TXV * 4;    // flat output columns per tile (= threads: one 
 constexpr int NTY = 4;          // thread rows in stages 0 and 2
 constexpr int NT = TXV * NTY;   // 256 threads
 
+// exact unsigned division by a runtime constant (Granlund-Montgomery, branch-free): n / d for all n < 2^32
+struct FastDiv {
+  uint32_t mul, sh1, sh2, d;
+  static FastDiv make(uint32_t d) {
+    uint32_t l = 0;
+    while ((1ull << l) < d) l++;
+    FastDiv f;
+    f.mul = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    f.sh1 = l < 1 ? l : 1;
+    f.sh2 = l > 0 ? l - 1 : 0;
+    f.d = d;
+    return f;
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const {
+    const uint32_t t = __umulhi(n, mul);
+    return (t + ((n - t) >> sh1)) >> sh2;
+  }
+};
+
 struct TParams {
   const void* in;
   void* out;  // float* or uint8_t* (epi.u8)
@@ -42,6 +61,8 @@ struct TParams {
   int pr;    // rows of patch / T buffers (max input rows per tile + KH - 1)
   int pcp;   // patch pitch in floats (max input flat cols per tile + (KW-1)*Ci, padded)
   int vec_store;  // rows of out are 16-byte aligned -> float4 stores
+  int vec_load;   // rows of in are 16-byte aligned (f32) -> 16-byte cp.async in stage 0
+  FastDiv dci, dcp;  // division by Ci (flat column -> pixel) and by lin.Cp (plane -> image)
   int64_t plane0;  // first plane of this launch (planes are launched in slabs of <= 65535)
 };
 
@@ -61,7 +82,10 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
   const int64_t plane = (int64_t)blockIdx.z + P.plane0;
   const int Ci = P.Ci;
   int64_t pn = plane, pp = 0;
-  if (P.lin.Cp > 1) { pn = plane / P.lin.Cp; pp = plane - pn * P.lin.Cp; }
+  if (P.lin.Cp > 1) {
+    if (plane < (1ll << 32)) { pn = P.dcp.div((uint32_t)plane); pp = plane - pn * P.lin.Cp; }
+    else { pn = plane / P.lin.Cp; pp = plane - pn * P.lin.Cp; }
+  }
   const in_t* ip = (const in_t*)P.in + pn * P.lin.stride_n + pp * P.lin.stride_p;
   const int64_t op = pn * P.lout.stride_n + pp * P.lout.stride_p;  // element offset
 
@@ -69,11 +93,12 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
   const int oy0 = tile_y * TY, oy1 = min(P.out_h, oy0 + TY);
   const int of0 = tile_x * TXF, of1 = min(P.out_wf, of0 + TXF);
   const int r0 = __ldg(P.h_start + oy0), r1 = __ldg(P.h_start + oy1 - 1) + __ldg(P.h_size + oy1 - 1);
-  const int oxa = of0 / Ci, oxb = (of1 - 1) / Ci;
+  const int oxa = (int)P.dci.div(of0), oxb = (int)P.dci.div(of1 - 1);
   const int c0 = __ldg(P.w_start + oxa) * Ci, c1 = (__ldg(P.w_start + oxb) + __ldg(P.w_size + oxb)) * Ci;
   const int nr = r1 - r0, nc = c1 - c0;
   const int prt = nr + KH - 1;             // T / patch rows touched by the unrolled tap loops
   const int pct = nc + (KW - 1) * Ci;      // patch columns touched
+  const int lead = (sizeof(in_t) == 4 && P.vec_load) ? (c0 & 3) : 0;  // aligned patches start `lead` columns early
 
   // ---- per-row records for stage 2
   if (tid < TY) {
@@ -97,6 +122,26 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
   {
     const in_t* src = ip + (int64_t)r0 * P.lin.stride_h + c0;
     if constexpr (sizeof(in_t) == 4) {
+      if (P.vec_load) {
+        // 16-byte copies: the patch starts at the aligned column below c0 (`lead` extra elements), its
+        // pitch is a multiple of 4 so chunk i of the CTA lands at patch + 4 i; the copy's src-size
+        // (0..16 bytes) zero-fills past the last valid column / row.
+        const in_t* srca = src - lead;
+        const int nq = P.pcp >> 2;      // chunks per patch row
+        const int nca = lead + nc;      // valid elements per patch row
+        const int total = prt * nq;
+        const int dr = NT / nq, dq = NT - dr * nq;
+        int r = tid / nq, q = tid - r * nq;
+        uint32_t d = (uint32_t)__cvta_generic_to_shared(patch) + 16u * tid;
+        for (int i = tid; i < total; i += NT, d += 16u * NT) {
+          int bytes = min(max((nca - 4 * q) * 4, 0), 16);
+          if (r >= nr) bytes = 0;
+          const in_t* g = bytes ? srca + (int64_t)r * P.lin.stride_h + 4 * q : srca;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(g), "r"(bytes) : "memory");
+          q += dq; r += dr;
+          if (q >= nq) { q -= nq; r++; }
+        }
+      } else {
       for (int r = ty; r < prt; r += NTY) {
         const in_t* srow = src + (int64_t)r * P.lin.stride_h;
         const uint32_t drow = (uint32_t)__cvta_generic_to_shared(patch + r * P.pcp);
@@ -106,6 +151,7 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
           const in_t* g = ok ? srow + c : src;  // any valid address when zero-filling
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(drow + 4u * c), "l"(g), "r"(ok ? 4 : 0) : "memory");
         }
+      }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     } else {
@@ -136,13 +182,13 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
   {
     const int of = of0 + tid;
     if (of < of1) {
-      const int ox = of / Ci;
+      const int ox = (int)P.dci.div(of);
       const int c = of - ox * Ci;
       const int st = __ldg(P.w_start + ox), sz = __ldg(P.w_size + ox);
       const float* wr = P.w_w + (int64_t)ox * P.w_pitch;
 #pragma unroll
       for (int k = 0; k < KW; k++) w[k] = k < sz ? __ldg(wr + k) : 0.f;
-      soff = st * Ci + c - c0;
+      soff = st * Ci + c - c0 + lead;
     } else {
 #pragma unroll
       for (int k = 0; k < KW; k++) w[k] = 0.f;
@@ -178,7 +224,7 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
     if constexpr (GEN) {
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        const int oxi = (ofv + i) / Ci;
+        const int oxi = (int)P.dci.div(ofv + i);
         cch[i] = (ofv + i) - oxi * Ci;
         coff[i] = P.epi.coloff(oxi, cch[i], Ci);
       }
@@ -243,9 +289,7 @@ int launch_ty(TParams& P, int64_t planes, const BandedAxis& ah, size_t smem_limi
 
 template <int KH, int KW, typename in_t>
 int launch_k(TParams& P, int64_t planes, const BandedAxis& ah, int nc_max, cudaStream_t stream) {
-  int pcp = nc_max + (KW - 1) * P.Ci;
-  pcp |= 1;  // odd pitch
-  P.pcp = pcp;
+  P.pcp = (nc_max + (KW - 1) * P.Ci + 3 + 3) & ~3;  // + up to 3 lead columns (aligned 16-byte copies); multiple of 4
   // tall tiles amortise the per-CTA setup when the patch stays small (upsampling-like gathers)
   if (P.epi.generic()) {  // decode-adjacent epilogue: its own instantiations, two tile heights
     int rg = launch_ty<KH, KW, 32, true, in_t>(P, planes, ah, 72 * 1024, stream);
@@ -299,6 +343,10 @@ int launch_tile(const void* in, int in_dtype, const Layout& lin, void* out, cons
     nc = std::max<int64_t>(nc, ((int64_t)aw.h_start[x1] + aw.h_size[x1] - aw.h_start[x0]) * Ci);
   }
   if (nc > 4096) return fail(AA_ERR_UNSUPPORTED, "tile: input patch too large; use the streaming/general path");
+  P.vec_load = in_dtype == AA_F32 && ((uintptr_t)in) % 16 == 0 && lin.stride_h % 4 == 0 && lin.stride_n % 4 == 0 &&
+               (lin.Cp == 1 || lin.stride_p % 4 == 0);
+  P.dci = FastDiv::make((uint32_t)Ci);
+  P.dcp = FastDiv::make((uint32_t)(lin.Cp > 0 ? lin.Cp : 1));
   P.vec_store = (((uintptr_t)out) % (epi.kind == 1 ? 4 : 16) == 0) && (lout.stride_h % 4 == 0) && (lout.stride_n % 4 == 0) &&
                 (lout.Cp == 1 || lout.stride_p % 4 == 0);
   if (in_dtype == AA_F32) return launch_in<float>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream);
