@@ -139,6 +139,12 @@ int forward_impl(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter
     // otherwise (downsampling): input-bound -> streaming kernel.
     const bool few_taps = th->xsize_max <= 7 && tw->xsize_max <= 7;
     if (few_taps && !(flags & AA_FLAG_FORCE_STREAM)) {
+      // mild vertical downsampling (1x..1.6x fewer rows): the band-walking variant; otherwise one tile per CTA
+      if (out->h <= in->h && in->h * 5 <= out->h * 8) {
+        rc = launch_band(in->data, in->dtype, lin, out->data, lout, fwd_axis(th.get()), fwd_axis(tw.get()), th->xsize_max,
+                         tw->xsize_max, epi, stream);
+        if (rc != AA_ERR_UNSUPPORTED) return rc;
+      }
       rc = launch_tile(in->data, in->dtype, lin, out->data, lout, fwd_axis(th.get()), fwd_axis(tw.get()), th->xsize_max,
                        tw->xsize_max, epi, stream);
       if (rc != AA_ERR_UNSUPPORTED) return rc;

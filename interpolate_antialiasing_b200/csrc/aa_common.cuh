@@ -125,6 +125,25 @@ struct OutEpi {
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 namespace aa {
+// exact unsigned division by a runtime constant (Granlund-Montgomery, branch-free): n / d for all n < 2^32
+struct FastDiv {
+  uint32_t mul, sh1, sh2, d;
+  static FastDiv make(uint32_t d) {
+    uint32_t l = 0;
+    while ((1ull << l) < d) l++;
+    FastDiv f;
+    f.mul = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    f.sh1 = l < 1 ? l : 1;
+    f.sh2 = l > 0 ? l - 1 : 0;
+    f.d = d;
+    return f;
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const {
+    const uint32_t t = __umulhi(n, mul);
+    return (t + ((n - t) >> sh1)) >> sh2;
+  }
+};
+
 __device__ __forceinline__ unsigned int aa_to_u8(float v, int round) {
   v = fminf(fmaxf(v, 0.f), 255.f);
   return (unsigned int)(round ? v + 0.5f : v);
@@ -170,6 +189,9 @@ int launch_general(const void* in, int in_dtype, const Layout& lin, void* out, i
 // Tile kernel for gathers with few taps (backward of downsampling, forward upsampling): input patch
 // in shared memory -> horizontal pass -> shared memory -> vertical pass -> 128-bit stores.  f32 out,
 // f32/u8 in.  Returns AA_ERR_UNSUPPORTED when the patch would not fit so the caller can fall back.
+// few taps, scale about 0.6x..1x (aa_band.cu): same contract as launch_tile
+int launch_band(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout,
+                const BandedAxis& ah, const BandedAxis& aw, int kh_max, int kw_max, OutEpi epi, cudaStream_t stream);
 int launch_tile(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout,
                 const BandedAxis& ah, const BandedAxis& aw, int kh_max, int kw_max, OutEpi epi, cudaStream_t stream);
 

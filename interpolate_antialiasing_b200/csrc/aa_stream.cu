@@ -181,10 +181,13 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
 template <int A, int VEC, typename in_t, int NT_>
 struct Cfg {
   static constexpr int NT = NT_;  // 256, or 128 when a whole row fits 128 threads (narrow images)
-  static constexpr int U = 4;
+  // rows in flight per thread.  uint8 rows are 4x fewer bytes per element, and the wide-tap uint8 shapes are
+  // limited to 2 CTAs/SM by shared memory anyway: they (A >= 4) take 8 rows and the 128-register budget that leaves.
+  static constexpr bool U8W = sizeof(in_t) == 1 && VEC == 8 && A >= 4;
+  static constexpr int U = U8W ? 8 : 4;
   static constexpr int TG = 4;  // buffered rows that trigger a horizontal phase
   // register budget: 64/thread when the accumulators are few (4 CTAs/SM at 256 threads), else fewer CTAs
-  static constexpr int MINB = ((A * VEC <= 12) ? 4 : ((A * VEC <= 32) ? 3 : 2)) * (256 / NT_);
+  static constexpr int MINB = (U8W ? 2 : (A * VEC <= 12) ? 4 : ((A * VEC <= 32) ? 3 : 2)) * (256 / NT_);
 };
 
 template <int A, int VEC, typename in_t, int NT_ = 256, bool GEN = false>

@@ -28,25 +28,6 @@ constexpr int TXF = TXV * 4;    // flat output columns per tile (= threads: one 
 constexpr int NTY = 4;          // thread rows in stages 0 and 2
 constexpr int NT = TXV * NTY;   // 256 threads
 
-// exact unsigned division by a runtime constant (Granlund-Montgomery, branch-free): n / d for all n < 2^32
-struct FastDiv {
-  uint32_t mul, sh1, sh2, d;
-  static FastDiv make(uint32_t d) {
-    uint32_t l = 0;
-    while ((1ull << l) < d) l++;
-    FastDiv f;
-    f.mul = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
-    f.sh1 = l < 1 ? l : 1;
-    f.sh2 = l > 0 ? l - 1 : 0;
-    f.d = d;
-    return f;
-  }
-  __device__ __forceinline__ uint32_t div(uint32_t n) const {
-    const uint32_t t = __umulhi(n, mul);
-    return (t + ((n - t) >> sh1)) >> sh2;
-  }
-};
-
 struct TParams {
   const void* in;
   void* out;  // float* or uint8_t* (epi.u8)

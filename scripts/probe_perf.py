@@ -91,6 +91,31 @@ if "sweep" in which:
                         print(f"sweep {mode} C={C} cl={cl} s={s} ERROR {e}", flush=True)
                     del x
 
+if "tile" in which:
+    # few-tap (tile kernel) cases only: forward 0.333x..2x bilinear/bicubic C=3 channels_first + backward of downsampling
+    Hin = Win = 1024
+    res = []
+    for mode in ("linear", "cubic"):
+        for s in (0.333, 0.5, 0.75, 1.0, 1.5, 2.0):
+            oh = ow = round(Hin * s)
+            per_img = 3 * (Hin * Win + oh * ow) * 4
+            N = max(1, int(1.0e9 // per_img) + 1)
+            x = torch.rand((N, 3, Hin, Win), generator=g, device=dev) * 255
+            out = capi.resize_forward(x, (oh, ow), mode, False, capi.FLAG_AUTO)
+            med, best = timeit(lambda: capi.resize_forward(x, (oh, ow), mode, False, capi.FLAG_AUTO, out=out), iters=5, warm=2)
+            res.append(f"{mode[0]}{s:g}:{N * per_img / med / 1e6 / PEAK * 100:.1f}")
+            del x, out
+    for mode in ("linear", "cubic"):
+        for (o, i) in ((128, 512), (512, 1024), (768, 1024)):
+            per_img = 3 * (o * o + i * i) * 4
+            N = max(1, int(3.0e8 // per_img) + 1)
+            go = torch.rand((N, 3, o, o), generator=g, device=dev)
+            capi.resize_backward(go, (N, 3, i, i), mode)
+            med, best = timeit(lambda: capi.resize_backward(go, (N, 3, i, i), mode), iters=5, warm=2)
+            res.append(f"b{mode[0]}{o}>{i}:{N * per_img / med / 1e6 / PEAK * 100:.1f}")
+            del go
+    print("tile " + os.environ.get("TAG", "") + " " + " ".join(res), flush=True)
+
 if "tma" in which:
     N = 64
     x = (torch.rand((N, 3, 1080, 1920), generator=g, device=dev) * 255).contiguous(memory_format=torch.channels_last)

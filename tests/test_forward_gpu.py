@@ -333,6 +333,41 @@ def test_extreme_shapes(cuda):
                     _close(y.cpu().numpy(), wantd)
 
 
+def test_band_walk_regime(cuda):
+    """Scales 0.62x..1x with few taps (the band-walking kernel of aa_band.cu): tall images so one CTA walks
+    several chunks and a band is cut into several segments, widths that defeat the 16-byte copies, output
+    heights that are not a multiple of the chunk, uint8 input, both layouts, a view into a larger batch."""
+    from interpolate_antialiasing_b200 import capi
+    g = torch.Generator().manual_seed(23)
+    cases = [
+        ((1, 3, 400, 300), (300, 225)),      # 0.75x, W*C % 4 == 0 channels_first
+        ((1, 3, 397, 301), (300, 226)),      # odd sizes: 4-byte copies
+        ((2, 1, 333, 520), (333, 520)),      # identity (1 tap)
+        ((1, 4, 512, 256), (330, 200)),      # 0.645x / 0.78x
+        ((3, 2, 130, 1100), (100, 1000)),    # several column bands
+        ((1, 3, 1000, 64), (777, 64)),       # many chunks per band, identity in W
+    ]
+    for shape, osize in cases:
+        for mode in ("linear", "cubic"):
+            x = torch.rand(shape, generator=g) * 255
+            for dt in (torch.float32, torch.uint8):
+                xs = x.to(dt)
+                want = O.forward(xs.float().numpy(), osize, mode, False)
+                for cl in (False, True):
+                    xc = xs.to(cuda)
+                    if cl:
+                        xc = xc.contiguous(memory_format=torch.channels_last)
+                    y = _run(capi, xc, osize, mode, False, capi.FLAG_AUTO)
+                    _close(y.cpu().numpy(), want)
+    # a batch slice of a larger tensor and the fused uint8 store
+    big = (torch.rand((4, 3, 240, 320), generator=g) * 255).to(cuda)
+    xs = big[1:3]
+    want = O.forward(xs.cpu().numpy(), (180, 240), "linear", False)
+    _close(_run(capi, xs, (180, 240), "linear", False, capi.FLAG_AUTO).cpu().numpy(), want)
+    y8 = capi.resize_forward(xs, (180, 240), "linear", False, capi.FLAG_AUTO, out_u8=True)
+    assert np.abs(y8.cpu().numpy().astype(np.int32) - np.clip(want, 0, 255).astype(np.uint8).astype(np.int32)).max() <= 1
+
+
 def test_random_fuzz_all_paths(cuda):
     """20 s of scripts/fuzz_parity.py: random shapes / scales / layouts / dtypes through every forward path
     (general path bit-exact, fast paths within tolerance) and the backward, against the oracle."""
