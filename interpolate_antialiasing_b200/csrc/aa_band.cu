@@ -226,26 +226,21 @@ __global__ void __launch_bounds__(NT) aa_band_kernel(const BParams P) {
     {
       const int keep = max(rdone - ra, 0);
       const int shift = ra - rbase;
-      if (shift > 0) {
+      if (shift > 0) {  // 4 rows at a time: the loads of a group are all ahead of its stores (shift >= 1)
         float* tcol = Ts + tid;
-        for (int j = 0; j < keep; j++) tcol[j * TXF] = tcol[(j + shift) * TXF];
+        for (int j = 0; j < keep; j += 4) {
+          float t[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) t[i] = tcol[(min(j + i, keep - 1) + shift) * TXF];
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            if (j + i < keep) tcol[(j + i) * TXF] = t[i];
+        }
       }
     }
     // ---- H pass: new rows [pa, rb) -> T rows (pa - ra)..
     {
-      const float* pb = patch;
-      const float* src[KW];  // one pointer per tap: the loop body is then LDS + FFMA only
-#pragma unroll
-      for (int k = 0; k < KW; k++) src[k] = pb + soff + k * Ci;
-      float* dst = Ts + (pa - ra) * TXF + tid;
-      const int n = rb - pa;
-#pragma unroll 4
-      for (int r = 0; r < n; r++) {
-        float a = 0.f;
-#pragma unroll
-        for (int k = 0; k < KW; k++) a = fmaf(src[k][r * pcp], w[k], a);
-        dst[r * TXF] = a;
-      }
+      aa_hpass<KW>(patch + soff, pcp, Ci, w, Ts + (pa - ra) * TXF + tid, TXF, rb - pa);
     }
     rbase = ra;
     rdone = rb;

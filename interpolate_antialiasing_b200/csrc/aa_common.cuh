@@ -125,6 +125,31 @@ struct OutEpi {
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 namespace aa {
+// Horizontal pass of the few-tap kernels (aa_tile.cu, aa_band.cu): n patch rows -> n rows of T for one flat
+// output column.  pb points at the column's first tap in patch row 0, taps are CI elements apart (CI = 0:
+// runtime interleave `ci`).  With a compile-time interleave the taps are immediate offsets of one row pointer,
+// so a row costs KW x (LDS + FFMA) + one address update instead of KW address updates.
+template <int KW, int CI>
+__device__ __forceinline__ void aa_hpass_rows(const float* pb, int pcp, int ci, const float (&w)[KW], float* dst, int tpitch, int n) {
+  const int step = CI ? CI : ci;
+#pragma unroll 4
+  for (int r = 0; r < n; r++) {
+    const float* p = pb + r * pcp;
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < KW; k++) a = fmaf(p[k * step], w[k], a);
+    dst[r * tpitch] = a;
+  }
+}
+template <int KW>
+__device__ __forceinline__ void aa_hpass(const float* pb, int pcp, int ci, const float (&w)[KW], float* dst, int tpitch, int n) {
+  switch (ci) {  // warp-uniform
+    case 1: aa_hpass_rows<KW, 1>(pb, pcp, ci, w, dst, tpitch, n); break;
+    case 3: aa_hpass_rows<KW, 3>(pb, pcp, ci, w, dst, tpitch, n); break;
+    case 4: aa_hpass_rows<KW, 4>(pb, pcp, ci, w, dst, tpitch, n); break;
+    default: aa_hpass_rows<KW, 0>(pb, pcp, ci, w, dst, tpitch, n); break;
+  }
+}
 // exact unsigned division by a runtime constant (Granlund-Montgomery, branch-free): n / d for all n < 2^32
 struct FastDiv {
   uint32_t mul, sh1, sh2, d;

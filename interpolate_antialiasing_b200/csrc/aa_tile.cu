@@ -178,20 +178,7 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
   if constexpr (sizeof(in_t) == 4) asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   // ---- stage 1: horizontal pass -> Ts
-  {
-    const float* src[KW];  // one pointer per tap: the loop body is then LDS + FFMA only
-#pragma unroll
-    for (int k = 0; k < KW; k++) src[k] = patch + soff + k * Ci;
-    float* dst = Ts + tid;
-    const int pcp = P.pcp;
-#pragma unroll 4
-    for (int r = 0; r < prt; r++) {
-      float a = 0.f;
-#pragma unroll
-      for (int k = 0; k < KW; k++) a = fmaf(src[k][r * pcp], w[k], a);
-      dst[r * TXF] = a;
-    }
-  }
+  aa_hpass<KW>(patch + soff, P.pcp, Ci, w, Ts + tid, TXF, prt);
   __syncthreads();
   // ---- stage 2: vertical pass + store
   const int ofv = of0 + 4 * tx;
