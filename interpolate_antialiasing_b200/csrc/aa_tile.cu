@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
   const int oxa = (int)P.dci.div(of0), oxb = (int)P.dci.div(of1 - 1);
   const int c0 = __ldg(P.w_start + oxa) * Ci, c1 = (__ldg(P.w_start + oxb) + __ldg(P.w_size + oxb)) * Ci;
   const int nr = r1 - r0, nc = c1 - c0;
-  const int prt = nr + KH - 1;             // T / patch rows touched by the unrolled tap loops
+  const int prt = nr + KH - 1;             // T rows touched by the unrolled vertical tap loop (rows >= nr are zero)
   const int pct = nc + (KW - 1) * Ci;      // patch columns touched
   const int lead = (sizeof(in_t) == 4 && P.vec_load) ? (c0 & 3) : 0;  // aligned patches start `lead` columns early
 
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
         const in_t* srca = src - lead;
         const int nq = P.pcp >> 2;      // chunks per patch row
         const int nca = lead + nc;      // valid elements per patch row
-        const int total = prt * nq;
+        const int total = nr * nq;
         const int dr = NT / nq, dq = NT - dr * nq;
         int r = tid / nq, q = tid - r * nq;
         uint32_t d = (uint32_t)__cvta_generic_to_shared(patch) + 16u * tid;
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
           if (q >= nq) { q -= nq; r++; }
         }
       } else {
-      for (int r = ty; r < prt; r += NTY) {
+      for (int r = ty; r < nr; r += NTY) {
         const in_t* srow = src + (int64_t)r * P.lin.stride_h;
         const uint32_t drow = (uint32_t)__cvta_generic_to_shared(patch + r * P.pcp);
         const bool rok = r < nr;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
     } else {
       constexpr int B = 8;
       const int ncol_it = (pct + TXV - 1) / TXV;       // column iterations per row
-      const int nrow_it = (prt - ty + NTY - 1) / NTY;  // row iterations of this thread
+      const int nrow_it = (nr - ty + NTY - 1) / NTY;  // row iterations of this thread
       const int total = nrow_it > 0 ? nrow_it * ncol_it : 0;
       for (int i0 = 0; i0 < total; i0 += B) {
         float v[B];
@@ -178,7 +178,9 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
   if constexpr (sizeof(in_t) == 4) asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   // ---- stage 1: horizontal pass -> Ts
-  aa_hpass<KW>(patch + soff, P.pcp, Ci, w, Ts + tid, TXF, prt);
+  aa_hpass<KW>(patch + soff, P.pcp, Ci, w, Ts + tid, TXF, nr);
+#pragma unroll
+  for (int r = 0; r < KH - 1; r++) Ts[(nr + r) * TXF + tid] = 0.f;  // rows past the last window: zero weight, finite value
   __syncthreads();
   // ---- stage 2: vertical pass + store
   const int ofv = of0 + 4 * tx;
