@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(NT) aa_band_kernel(const BParams P) {
 #pragma unroll
         for (int k = 0; k < KH; k++) {
           const float4 v = src[k * TXV];
-          a.x = fmaf(v.x, rc[k], a.x); a.y = fmaf(v.y, rc[k], a.y); a.z = fmaf(v.z, rc[k], a.z); a.w = fmaf(v.w, rc[k], a.w);
+          aa_fma4(a, v, rc[k]);
         }
         if (!GEN && full && P.epi.kind == 0) {
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + dst + ofv) = a;

@@ -132,14 +132,31 @@ namespace aa {
 template <int KW, int CI>
 __device__ __forceinline__ void aa_hpass_rows(const float* pb, int pcp, int ci, const float (&w)[KW], float* dst, int tpitch, int n) {
   const int step = CI ? CI : ci;
-#pragma unroll 4
-  for (int r = 0; r < n; r++) {
+  int r = 0;
+  // two rows per step: packed FFMA2 (two fp32 FMAs per issue slot, the column's weight as the scalar operand)
+#pragma unroll 2
+  for (; r + 2 <= n; r += 2) {
+    const float* p = pb + r * pcp;
+    float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < KW; k++) a = __ffma2_rn(make_float2(w[k], w[k]), make_float2(p[k * step], p[pcp + k * step]), a);
+    dst[r * tpitch] = a.x;
+    dst[(r + 1) * tpitch] = a.y;
+  }
+  if (r < n) {
     const float* p = pb + r * pcp;
     float a = 0.f;
 #pragma unroll
     for (int k = 0; k < KW; k++) a = fmaf(p[k * step], w[k], a);
     dst[r * tpitch] = a;
   }
+}
+// Vertical taps of the few-tap kernels: a += w * v for 4 adjacent columns (two FFMA2)
+__device__ __forceinline__ void aa_fma4(float4& a, const float4& v, float w) {
+  const float2 w2 = make_float2(w, w);
+  const float2 lo = __ffma2_rn(w2, make_float2(v.x, v.y), make_float2(a.x, a.y));
+  const float2 hi = __ffma2_rn(w2, make_float2(v.z, v.w), make_float2(a.z, a.w));
+  a = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 template <int KW>
 __device__ __forceinline__ void aa_hpass(const float* pb, int pcp, int ci, const float (&w)[KW], float* dst, int tpitch, int n) {
