@@ -1,5 +1,6 @@
 // aa_api.cu -- the C ABI (include/aa_resize.h): validation, table cache lookups, path selection.
 // No torch types, no exceptions across the boundary, no CPU fallback.
+#include <cstdlib>
 #include <string.h>
 
 #include <mutex>
