@@ -45,7 +45,7 @@ namespace {
 // MINB  CTAs per SM the register allocation must allow
 // Shared memory holds up to P.vr vertically-filtered rows; the horizontal phase runs at the end of a
 // U-row batch once at least P.tg rows are buffered (host guarantees tg - 1 + max flushes per batch <= vr).
-template <int A, int VEC, typename in_t, int NT, int U, int MINB, bool GEN>
+template <int A, int VEC, typename in_t, int NT, int U, int MINB, bool GEN, bool PAD>
 __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
   extern __shared__ __align__(16) float smem[];
   constexpr int RPT = 4;
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
   using RawT = typename Raw<in_t, VEC>::T;
   constexpr int RN = Raw<in_t, VEC>::N;
   float* Vs = smem;                                  // [vr][vw]
-  float2* Wp = reinterpret_cast<float2*>(Vs + (size_t)P.vr * P.vw);                       // [pairs][kp]
+  float2* Wp = reinterpret_cast<float2*>(Vs + (size_t)P.vr * vs_pitch(P.vw, PAD));                       // [pairs][kp]
   int4* pinfo = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(Wp) + P.wtab_bytes + 15) & ~(uintptr_t)15);      // [pairs * Ci]
 
   const int t = threadIdx.x;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
     const in_t* ip = (const in_t*)P.in + (plane / P.lin.Cp) * P.lin.stride_n + (plane % P.lin.Cp) * P.lin.stride_p + fmy + yA * stride_h;
     const float4* rp = reinterpret_cast<const float4*>(P.slot_h) + yA * RS4;
     const int64_t op = (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p;  // element offset of the plane
-    float* vdst = Vs + VEC * t;
+    float* vdst = Vs + vs_pos(VEC * t, PAD);  // this thread's columns in Vs row 0
     float* vptr = vdst;          // where the next finished row goes
     const bool vstore = valid;   // (kept in a predicate-friendly local)
 
@@ -123,8 +123,15 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
 #pragma unroll 1
         do {
           if (o >= oyA && o < oyB) {
-            if (vstore) store_vec<VEC>(vptr, acc[0]);
-            vptr += VW;
+            if (vstore) {
+              if constexpr (PAD) {  // padded rows: the thread's columns stay contiguous but lose their 16-byte alignment
+#pragma unroll
+                for (int e = 0; e < VEC; e++) vptr[e] = acc[0][e];
+              } else {
+                store_vec<VEC>(vptr, acc[0]);
+              }
+            }
+            vptr += vs_pitch(VW, PAD);
             cnt++;
           }
 #pragma unroll
@@ -140,7 +147,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
     // horizontal filter over the buffered rows [gbase, gbase+cnt)
     auto hphase = [&]() {
       __syncthreads();
-      hphase_run<RPT, VW, GEN>(P, Vs, Wp, pinfo, op, strip_npc, role, gbase, cnt);
+      hphase_run<RPT, VW, GEN, PAD>(P, Vs, Wp, pinfo, op, strip_npc, role, gbase, cnt);
       __syncthreads();
       gbase += cnt;
       cnt = 0;
@@ -178,7 +185,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
   }
 }
 
-template <int A, int VEC, typename in_t, int NT_>
+template <int A, int VEC, typename in_t, int NT_, bool PAD = false>
 struct Cfg {
   static constexpr int NT = NT_;  // 256, or 128 when a whole row fits 128 threads (narrow images)
   // rows in flight per thread.  uint8 rows are 4x fewer bytes per element, and the wide-tap uint8 shapes are
@@ -187,7 +194,8 @@ struct Cfg {
   static constexpr int U = U8W ? 8 : 4;
   static constexpr int TG = 4;  // buffered rows that trigger a horizontal phase
   // register budget: 64/thread when the accumulators are few (4 CTAs/SM at 256 threads), else fewer CTAs
-  static constexpr int MINB = (U8W ? 2 : (A * VEC <= 12) ? 4 : ((A * VEC <= 32) ? 3 : 2)) * (256 / NT_);
+  // (scripts/sass_lint.py checks that ptxas still issues all U row loads before the first FMA under each budget)
+  static constexpr int MINB = (U8W ? 2 : (A * VEC <= 12 && !PAD && A < 6) ? 4 : ((A * VEC <= 32 && (A < 6 || VEC < 4)) ? 3 : 2)) * (256 / NT_);
 };
 
 template <int A, int VEC, typename in_t, int NT_ = 256, bool GEN = false>
@@ -199,18 +207,31 @@ int launch_cfg(SParams& P, const StreamTables& T, int device, cudaStream_t strea
   } else if constexpr (!GEN) {
     if (P.epi.generic()) return fail(AA_ERR_UNSUPPORTED, "stream: generic epilogue not instantiated for this shape");
   }
-  auto kern = aa_stream_kernel<A, VEC, in_t, C::NT, C::U, C::MINB, GEN>;
+  // PAD (bank-conflict-free padded row buffer) exists for the wide-vector shapes; plan_stream decides per table
+  constexpr bool PADDABLE = !GEN && NT_ == 256 && ((VEC == 4 && sizeof(in_t) == 4) || (VEC == 8 && sizeof(in_t) == 1));
+  auto kern = aa_stream_kernel<A, VEC, in_t, C::NT, C::U, C::MINB, GEN, false>;
   const PlanKey key{T.key_h, T.key_w, P.Ci, (T.dir << 29) | (GEN ? (1 << 28) : 0) | (NT_ << 16) | (A << 8) | (VEC << 2) | (int)sizeof(in_t) % 4};
   Plan pl;
   if (!plan_lookup(key, &pl)) {
     P.in_pitch = 0;
     int rc = plan_stream(P, T, C::NT * VEC, VEC, VEC, C::U, C::TG);
     if (rc != AA_OK) return rc;
-    const size_t smem_ = sizeof(float) * (size_t)P.vr * P.vw + strip_table_bytes(P);
+    if (!PADDABLE) P.pad = 0;
+    const size_t smem_ = sizeof(float) * (size_t)P.vr * vs_pitch(P.vw, P.pad != 0) + strip_table_bytes(P);
     if (smem_ > 200 * 1024) return fail(AA_ERR_UNSUPPORTED, "stream: shared memory plan too large");
-    AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int occ = 0, sms = 0;
-    AA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NT, smem_));
+    if constexpr (PADDABLE) {
+      if (P.pad) {
+        using CP = Cfg<A, VEC, in_t, NT_, true>;
+        auto kp = aa_stream_kernel<A, VEC, in_t, CP::NT, CP::U, CP::MINB, GEN, true>;
+        AA_CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        AA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kp, C::NT, smem_));
+      }
+    }
+    if (!P.pad) {
+      AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      AA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NT, smem_));
+    }
     AA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     if (occ < 1) return fail(AA_ERR_UNSUPPORTED, "stream: kernel does not fit on an SM");
     pl = plan_from(P, smem_, occ * sms);
@@ -225,6 +246,14 @@ int launch_cfg(SParams& P, const StreamTables& T, int device, cudaStream_t strea
   static const int gmul = [] { const char* e = getenv("AA_STREAM_GRID_MUL"); return e ? std::max(1, atoi(e)) : 2; }();  // tuning knob
   const int64_t want = std::min<int64_t>((int64_t)pl.max_grid * gmul, std::max<int64_t>(pl.max_grid, P.total_units / P.oH));
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(want, P.total_units / min_units));
+  if constexpr (PADDABLE) {
+    if (P.pad) {
+      using CP = Cfg<A, VEC, in_t, NT_, true>;
+      aa_stream_kernel<A, VEC, in_t, CP::NT, CP::U, CP::MINB, GEN, true><<<(unsigned)grid, C::NT, smem, stream>>>(P);
+      AA_LAUNCH_CHECK("aa_stream_kernel");
+      return AA_OK;
+    }
+  }
   kern<<<(unsigned)grid, C::NT, smem, stream>>>(P);
   AA_LAUNCH_CHECK("aa_stream_kernel");
   return AA_OK;

@@ -1,6 +1,8 @@
 // aa_stream_common.cuh -- pieces shared by the two variants of the streaming forward kernel
 // (aa_stream.cu: plain 128-bit global loads; aa_stream_tma.cu: cp.async.bulk row staging).
 #pragma once
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 
 #include "aa_common.cuh"
@@ -25,7 +27,8 @@ struct SParams {
   int Kw;
   int n_strips, strip_ox;
   int64_t total_units;  // planes * n_strips * oH
-  int vw;               // shared-memory row pitch of Vs in floats
+  int vw;               // columns of a Vs row (strip capacity); the row pitch is vs_pitch(vw)
+  int pad;              // 1: Vs rows are stored with one pad word per 32 (bank-conflict-free gathers at power-of-two strides)
   int vr;               // rows of Vs
   int tg;               // buffered rows that trigger a horizontal phase
   int aln;              // alignment (elements) of a strip's first flat element
@@ -139,6 +142,12 @@ template <int VEC> __device__ __forceinline__ void store_vec(float* dst, const f
 //   pinfo[pair*Ci+c] int4   {first tap's offset in a Vs row, pair*KP, union window length | has_b<<16 | c<<20,
 //                            offset of column a inside an output row (OutEpi::coloff)}
 // so the phase itself needs no integer division and no per-column table lookups.
+// Row pitch of Vs (floats) and the position of column f inside a row.  With `pad` one unused word follows
+// every 32: a gather whose lanes are 4, 8, 16... words apart (integer scale factors) then spreads over all 32
+// banks instead of 8, 4, 2.  Chosen per plan (plan_stream) from the strip's actual window starts.
+__host__ __device__ constexpr int vs_pitch(int vw, bool pad) { return pad ? vw + vw / 32 : vw; }
+__device__ __forceinline__ int vs_pos(int f, int pad) { return pad ? f + (f >> 5) : f; }
+
 struct HRole {        // which (row group, pair-column) items a thread owns; fixed per strip
   int rg0, rg_par;    // first row group and stride over row groups
   int cf0, cf_step;   // first pair-column and stride over pair-columns
@@ -202,7 +211,7 @@ __device__ __forceinline__ void strip_setup(const SParams& P, int t, int nthread
 // Gather over the buffered rows [0, cnt) of Vs -> output rows gbase..gbase+cnt-1.  Trip counts are
 // warp-uniform (longest union window in the warp); past a lane's own window the weights read are the
 // zero padding and the data pointer stops advancing, so no element outside the true windows is touched.
-template <int RPT, int VW, bool GEN>
+template <int RPT, int VW, bool GEN, bool PAD>
 __device__ __forceinline__ void hphase_run_pairs(const float* __restrict__ Vs, const float2* __restrict__ Wp,
                                            const int4* __restrict__ pinfo, void* __restrict__ op, int64_t op_off,
                                            const OutEpi& epi, int64_t out_stride_h, int Ci, int npc, const HRole role, int gbase,
@@ -216,19 +225,24 @@ __device__ __forceinline__ void hphase_run_pairs(const float* __restrict__ Vs, c
       const int len = act ? (pi.z & 0xffff) : 1;
       const int lenm = __reduce_max_sync(0xffffffffu, len);
       const float2* wr = Wp + pi.y;
-      const float* vp = Vs + (rg * RPT) * VW + pi.x;
+      constexpr int VP = vs_pitch(VW, PAD);
+      const float* vrow = Vs + (rg * RPT) * VP;   // warp-uniform
+      const float* vp = vrow + pi.x;
+      uint32_t fb = 4u * (uint32_t)pi.x;           // PAD: byte offset of the tap's column, before padding
       float2 h[RPT];
 #pragma unroll
       for (int r = 0; r < RPT; r++) h[r] = make_float2(0.f, 0.f);
 #pragma unroll 4
       for (int j = 0; j < lenm; j++) {
         const float2 w2 = wr[j];
+        if constexpr (PAD) vp = reinterpret_cast<const float*>(reinterpret_cast<const char*>(vrow) + fb + ((fb >> 7) << 2));
 #pragma unroll
         for (int r = 0; r < RPT; r++) {
-          const float v = vp[r * VW];
+          const float v = vp[r * VP];
           h[r] = __ffma2_rn(make_float2(v, v), w2, h[r]);
         }
-        vp += (j + 1 < len) ? Ci : 0;
+        if constexpr (PAD) fb += (j + 1 < len) ? 4u * Ci : 0u;
+        else vp += (j + 1 < len) ? Ci : 0;
       }
       if (act) {
         const int64_t dst = op_off + (int64_t)(gbase + rg * RPT) * out_stride_h + pi.w;
@@ -246,7 +260,7 @@ __device__ __forceinline__ void hphase_run_pairs(const float* __restrict__ Vs, c
   }
 }
 // single-column form (P.pairs == 0): one item = one flat output column x RPT rows, FFMA2 over row pairs
-template <int RPT, int VW, bool GEN>
+template <int RPT, int VW, bool GEN, bool PAD>
 __device__ __forceinline__ void hphase_run_single(const float* __restrict__ Vs, const float* __restrict__ Ws,
                                                   const int4* __restrict__ pinfo, void* __restrict__ op, int64_t op_off,
                                                   const OutEpi& epi, int64_t out_stride_h, int Ci, int nof, const HRole role,
@@ -260,7 +274,10 @@ __device__ __forceinline__ void hphase_run_single(const float* __restrict__ Vs, 
       const int xs = act ? (ci.z & 0xfffff) : 1;
       const int xsm = __reduce_max_sync(0xffffffffu, xs);
       const float* wr = Ws + ci.y;
-      const float* vp = Vs + (rg * RPT) * VW + ci.x;
+      constexpr int VP = vs_pitch(VW, PAD);
+      const float* vrow = Vs + (rg * RPT) * VP;
+      const float* vp = vrow + ci.x;
+      uint32_t fb = 4u * (uint32_t)ci.x;
       float h[RPT];
 #pragma unroll
       for (int r = 0; r < RPT; r++) h[r] = 0.f;
@@ -268,13 +285,15 @@ __device__ __forceinline__ void hphase_run_single(const float* __restrict__ Vs, 
       for (int j = 0; j < xsm; j++) {
         const float wj = wr[j];
         const float2 w2 = make_float2(wj, wj);
+        if constexpr (PAD) vp = reinterpret_cast<const float*>(reinterpret_cast<const char*>(vrow) + fb + ((fb >> 7) << 2));
 #pragma unroll
         for (int r = 0; r < RPT; r += 2) {
-          const float2 q = __ffma2_rn(w2, make_float2(vp[r * VW], vp[(r + 1) * VW]), make_float2(h[r], h[r + 1]));
+          const float2 q = __ffma2_rn(w2, make_float2(vp[r * VP], vp[(r + 1) * VP]), make_float2(h[r], h[r + 1]));
           h[r] = q.x;
           h[r + 1] = q.y;
         }
-        vp += (j + 1 < xs) ? Ci : 0;
+        if constexpr (PAD) fb += (j + 1 < xs) ? 4u * Ci : 0u;
+        else vp += (j + 1 < xs) ? Ci : 0;
       }
       if (act) {
         const int64_t dst = op_off + (int64_t)(gbase + rg * RPT) * out_stride_h + ci.w;
@@ -286,11 +305,11 @@ __device__ __forceinline__ void hphase_run_single(const float* __restrict__ Vs, 
     }
   }
 }
-template <int RPT, int VW, bool GEN>
+template <int RPT, int VW, bool GEN, bool PAD>
 __device__ __forceinline__ void hphase_run(const SParams& P, const float* Vs, const float2* Wp, const int4* pinfo, int64_t op_off,
                                            int npc, const HRole role, int gbase, int cnt) {
-  if (P.pairs) hphase_run_pairs<RPT, VW, GEN>(Vs, Wp, pinfo, P.out, op_off, P.epi, P.lout.stride_h, P.Ci, npc, role, gbase, cnt);
-  else hphase_run_single<RPT, VW, GEN>(Vs, reinterpret_cast<const float*>(Wp), pinfo, P.out, op_off, P.epi, P.lout.stride_h, P.Ci, npc, role, gbase, cnt);
+  if (P.pairs) hphase_run_pairs<RPT, VW, GEN, PAD>(Vs, Wp, pinfo, P.out, op_off, P.epi, P.lout.stride_h, P.Ci, npc, role, gbase, cnt);
+  else hphase_run_single<RPT, VW, GEN, PAD>(Vs, reinterpret_cast<const float*>(Wp), pinfo, P.out, op_off, P.epi, P.lout.stride_h, P.Ci, npc, role, gbase, cnt);
 }
 // bytes of the strip tables (after Vs) for a plan
 inline size_t strip_table_bytes(const SParams& P) {
@@ -356,6 +375,25 @@ inline int plan_stream(SParams& P, const StreamTables& T, int cap, int aln, int 
   P.pairs = (int64_t)strip_ox * Ci >= 256 ? 1 : 0;  // enough independent items per row group to halve them
   P.wtab_bytes = P.pairs ? (int)((size_t)((strip_ox + 1) / 2) * P.kp * sizeof(float2)) : (int)((size_t)strip_ox * P.Kw * sizeof(float));
   if (P.kp >= (1 << 16) || (int64_t)((strip_ox + 1) / 2) * P.kp >= (1ll << 30)) return fail(AA_ERR_UNSUPPORTED, "stream: window too long");
+  // Bank picture of the gather: the first 32 items of the first strip read, at tap 0, the columns below.
+  // Pad the rows when that would at least halve a >= 4-way conflict.
+  {
+    auto worst = [&](bool pad) {
+      int cnt[32] = {0}, w = 0;
+      const int64_t f0 = ((int64_t)T.hw_start[0] * Ci) & ~(int64_t)(aln - 1);
+      const int nitem = P.pairs ? (strip_ox + 1) / 2 * Ci : strip_ox * Ci;
+      for (int l = 0; l < 32 && l < nitem; l++) {
+        const int o = P.pairs ? 2 * (l / Ci) : l / Ci, c = l % Ci;
+        if (o >= oW) break;
+        const int64_t f = (int64_t)T.hw_start[o] * Ci + c - f0;
+        const int64_t pos = pad ? f + (f >> 5) : f;
+        w = std::max(w, ++cnt[pos & 31]);
+      }
+      return w;
+    };
+    const int w0 = worst(false), w1 = worst(true);
+    P.pad = (w0 >= 4 && 2 * w1 <= w0) ? 1 : 0;
+  }
   P.tg = tg;
   P.vr = (P.tg - 1 + fmax + 3) / 4 * 4;
   if (P.vr > 32) return fail(AA_ERR_UNSUPPORTED, "stream: too many output rows finish per input batch (upsampling in H)");
@@ -376,7 +414,7 @@ struct PlanKey {
   }
 };
 struct Plan {
-  int n_strips, strip_ox, vw, vr, tg, aln, in_pitch, kp, pairs, wtab_bytes;
+  int n_strips, strip_ox, vw, vr, tg, aln, in_pitch, kp, pairs, wtab_bytes, pad;
   size_t smem;
   int max_grid;  // SMs * resident CTAs per SM
 };
@@ -385,6 +423,7 @@ void plan_store(const PlanKey& k, const Plan& p);
 void plan_clear();
 inline void plan_apply(SParams& P, const Plan& pl) {
   P.n_strips = pl.n_strips; P.strip_ox = pl.strip_ox; P.vw = pl.vw; P.vr = pl.vr; P.tg = pl.tg; P.aln = pl.aln;
+  P.pad = pl.pad;
   P.in_pitch = pl.in_pitch;
   P.kp = pl.kp;
   P.pairs = pl.pairs;
@@ -392,7 +431,7 @@ inline void plan_apply(SParams& P, const Plan& pl) {
   P.total_units = P.lin.planes * pl.n_strips * P.oH;
 }
 inline Plan plan_from(const SParams& P, size_t smem, int max_grid) {
-  return Plan{P.n_strips, P.strip_ox, P.vw, P.vr, P.tg, P.aln, P.in_pitch, P.kp, P.pairs, P.wtab_bytes, smem, max_grid};
+  return Plan{P.n_strips, P.strip_ox, P.vw, P.vr, P.tg, P.aln, P.in_pitch, P.kp, P.pairs, P.wtab_bytes, P.pad, smem, max_grid};
 }
 
 }  // namespace stream_detail

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
     };
     auto hphase = [&]() {
       consumer_sync();
-      hphase_run<RPT, VW, false>(P, Vs, Wp, pinfo, op, strip_npc, role, gbase, cnt);
+      hphase_run<RPT, VW, false, false>(P, Vs, Wp, pinfo, op, strip_npc, role, gbase, cnt);
       consumer_sync();
       gbase += cnt;
       cnt = 0;
@@ -249,6 +249,7 @@ int launch_tma_cfg(SParams& P, const StreamTables& T, int device, cudaStream_t s
   if (!plan_lookup(key, &pl)) {
     int rc = plan_stream(P, T, NTC * VEC, 16 / ES, VEC, R, 4);
     if (rc != AA_OK) return rc;
+    P.pad = 0;  // the padded row buffer exists in the plain-load variant only
     P.in_pitch = (P.vw * ES + 15) & ~15;
     const size_t smem_ = (size_t)STAGES * R * P.in_pitch + sizeof(float) * (size_t)P.vr * P.vw + strip_table_bytes(P) + 8 + 16 * STAGES;
     if (smem_ > 200 * 1024) return fail(AA_ERR_UNSUPPORTED, "stream/tma: shared memory plan too large");

@@ -94,3 +94,15 @@ def test_extension_exports_reference_names():
     # /root/reference/step_two_dot_two/extension_interpolate.cpp:46-51
     for name in ("linear_forward", "nearest_forward", "cubic_forward", "linear_backward"):
         assert callable(getattr(m, name))
+
+
+def test_stream_kernels_issue_row_loads_before_first_fma():
+    """scripts/sass_lint.py on the built library: in every streaming-kernel instantiation the U input rows of
+    a batch are requested before the first FMA (ptxas sinks loads when the register budget of a shape is too
+    tight, which costs ~15 % on the headline config).  The 6-accumulator uint8 shape is the known exception."""
+    import subprocess, sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "sass_lint.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    flagged = [l for l in r.stdout.splitlines() if "<--" in l]
+    assert flagged and all(l.startswith("A=6 VEC=8 h") for l in flagged) or not flagged, "\n".join(flagged)
+    assert any(l.startswith("A=3 VEC=4 f NT=256 U=4 GEN=0 PAD=0: 4 data loads") for l in r.stdout.splitlines())
