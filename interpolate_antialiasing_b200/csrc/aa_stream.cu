@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
     const in_t* ip = (const in_t*)P.in + (plane / P.lin.Cp) * P.lin.stride_n + (plane % P.lin.Cp) * P.lin.stride_p + fmy + yA * stride_h;
     const float4* rp = reinterpret_cast<const float4*>(P.slot_h) + yA * RS4;
     const int64_t op = (plane / P.lout.Cp) * P.lout.stride_n + (plane % P.lout.Cp) * P.lout.stride_p;  // element offset of the plane
-    float* vdst = Vs + vs_pos(VEC * t, PAD);  // this thread's columns in Vs row 0
+    float* vdst = Vs + vs_pos(VEC * t, PAD ? P.pad : 0);  // this thread's columns in Vs row 0
     float* vptr = vdst;          // where the next finished row goes
     const bool vstore = valid;   // (kept in a predicate-friendly local)
 

@@ -28,12 +28,14 @@ struct SParams {
   int n_strips, strip_ox;
   int64_t total_units;  // planes * n_strips * oH
   int vw;               // columns of a Vs row (strip capacity); the row pitch is vs_pitch(vw)
-  int pad;              // 1: Vs rows are stored with one pad word per 32 (bank-conflict-free gathers at power-of-two strides)
+  int pad;              // q = 0/1/2/4: Vs rows are stored with q pad words per 32 columns (bank-conflict-free gathers at
+                        // power-of-two lane strides); pos(f) = f + (f >> 5) * q
   int vr;               // rows of Vs
   int tg;               // buffered rows that trigger a horizontal phase
   int aln;              // alignment (elements) of a strip's first flat element
   int in_pitch;         // TMA variant: bytes between staged input rows in shared memory
-  int kp;               // pitch of the paired weight table = Kw + max(xmin[o+1]-xmin[o]) over pairs
+  int kp;               // pitch of the strip's weight table, made odd so that lanes (= different columns) reading tap j
+                        // hit different banks: pairs: Kw + max(xmin[o+1]-xmin[o]) (float2 units); single columns: Kw (floats)
   int pairs;            // horizontal phase computes pairs of adjacent output columns (wide strips)
   int wtab_bytes;       // bytes reserved for the weight table (pinfo follows, 16-byte aligned)
 };
@@ -142,11 +144,13 @@ template <int VEC> __device__ __forceinline__ void store_vec(float* dst, const f
 //   pinfo[pair*Ci+c] int4   {first tap's offset in a Vs row, pair*KP, union window length | has_b<<16 | c<<20,
 //                            offset of column a inside an output row (OutEpi::coloff)}
 // so the phase itself needs no integer division and no per-column table lookups.
-// Row pitch of Vs (floats) and the position of column f inside a row.  With `pad` one unused word follows
-// every 32: a gather whose lanes are 4, 8, 16... words apart (integer scale factors) then spreads over all 32
-// banks instead of 8, 4, 2.  Chosen per plan (plan_stream) from the strip's actual window starts.
-__host__ __device__ constexpr int vs_pitch(int vw, bool pad) { return pad ? vw + vw / 32 : vw; }
-__device__ __forceinline__ int vs_pos(int f, int pad) { return pad ? f + (f >> 5) : f; }
+// Row pitch of Vs (floats) and the position of column f inside a row.  With padding, q unused words follow
+// every 32 columns: a gather whose lanes are 4, 8, 16, 32... words apart (integer scale factors, times the channel
+// interleave) then spreads over all 32 banks instead of 8, 4, 2, 1.  q is chosen per plan (plan_stream) from the
+// strip's actual window starts; padded kernels reserve the pitch of the largest q.
+constexpr int kPadMaxQ = 4;
+__host__ __device__ constexpr int vs_pitch(int vw, bool pad) { return pad ? vw + (vw / 32) * kPadMaxQ : vw; }
+__device__ __forceinline__ int vs_pos(int f, int q) { return f + (f >> 5) * q; }
 
 struct HRole {        // which (row group, pair-column) items a thread owns; fixed per strip
   int rg0, rg_par;    // first row group and stride over row groups
@@ -168,7 +172,7 @@ __device__ __forceinline__ HRole hphase_role(int t, int nthreads, int npc) {
 }
 // Called by all `nthreads` threads between two barriers when the CTA moves to a new strip.
 // P.pairs == 0 builds the single-column form of the same tables instead (narrow strips, where halving
-// the number of independent items would starve the phase): Wp is then a float array with pitch Kw.
+// the number of independent items would starve the phase): Wp is then a float array with pitch KP.
 __device__ __forceinline__ void strip_setup(const SParams& P, int t, int nthreads, int ox0, int ox1, float2* Wp, int4* pinfo,
                                             int* fl0_out, int* npc_out) {
   const int Ci = P.Ci, Kw = P.Kw, KP = P.kp;
@@ -177,10 +181,13 @@ __device__ __forceinline__ void strip_setup(const SParams& P, int t, int nthread
   *fl0_out = fl0;
   if (!P.pairs) {
     float* Ws = reinterpret_cast<float*>(Wp);
-    for (int i = t; i < nox * Kw; i += nthreads) Ws[i] = __ldg(P.w_w + (int64_t)ox0 * Kw + i);
+    for (int i = t; i < nox * KP; i += nthreads) {
+      const int oxl = i / KP, j = i - oxl * KP;
+      Ws[i] = j < Kw ? __ldg(P.w_w + (int64_t)(ox0 + oxl) * Kw + j) : 0.f;
+    }
     for (int cf = t; cf < nox * Ci; cf += nthreads) {
       const int oxl = cf / Ci, c = cf - oxl * Ci;
-      pinfo[cf] = make_int4(__ldg(P.xmin_w + ox0 + oxl) * Ci + c - fl0, oxl * Kw, __ldg(P.xsize_w + ox0 + oxl) | (c << 20),
+      pinfo[cf] = make_int4(__ldg(P.xmin_w + ox0 + oxl) * Ci + c - fl0, oxl * KP, __ldg(P.xsize_w + ox0 + oxl) | (c << 20),
                             P.epi.coloff(ox0 + oxl, c, Ci));
     }
     *npc_out = nox * Ci;
@@ -215,7 +222,7 @@ template <int RPT, int VW, bool GEN, bool PAD>
 __device__ __forceinline__ void hphase_run_pairs(const float* __restrict__ Vs, const float2* __restrict__ Wp,
                                            const int4* __restrict__ pinfo, void* __restrict__ op, int64_t op_off,
                                            const OutEpi& epi, int64_t out_stride_h, int Ci, int npc, const HRole role, int gbase,
-                                           int cnt) {
+                                           int cnt, int padsh) {
   const int nrg = (cnt + RPT - 1) / RPT;
   for (int rg = role.rg0; rg < nrg; rg += role.rg_par) {
     for (int cfb = role.cf0 - (role.cf0 & 31); cfb < npc; cfb += role.cf_step) {
@@ -235,7 +242,7 @@ __device__ __forceinline__ void hphase_run_pairs(const float* __restrict__ Vs, c
 #pragma unroll 4
       for (int j = 0; j < lenm; j++) {
         const float2 w2 = wr[j];
-        if constexpr (PAD) vp = reinterpret_cast<const float*>(reinterpret_cast<const char*>(vrow) + fb + ((fb >> 7) << 2));
+        if constexpr (PAD) vp = reinterpret_cast<const float*>(reinterpret_cast<const char*>(vrow) + fb + ((fb >> 7) << padsh));
 #pragma unroll
         for (int r = 0; r < RPT; r++) {
           const float v = vp[r * VP];
@@ -264,7 +271,7 @@ template <int RPT, int VW, bool GEN, bool PAD>
 __device__ __forceinline__ void hphase_run_single(const float* __restrict__ Vs, const float* __restrict__ Ws,
                                                   const int4* __restrict__ pinfo, void* __restrict__ op, int64_t op_off,
                                                   const OutEpi& epi, int64_t out_stride_h, int Ci, int nof, const HRole role,
-                                                  int gbase, int cnt) {
+                                                  int gbase, int cnt, int padsh) {
   const int nrg = (cnt + RPT - 1) / RPT;
   for (int rg = role.rg0; rg < nrg; rg += role.rg_par) {
     for (int cfb = role.cf0 - (role.cf0 & 31); cfb < nof; cfb += role.cf_step) {
@@ -285,7 +292,7 @@ __device__ __forceinline__ void hphase_run_single(const float* __restrict__ Vs, 
       for (int j = 0; j < xsm; j++) {
         const float wj = wr[j];
         const float2 w2 = make_float2(wj, wj);
-        if constexpr (PAD) vp = reinterpret_cast<const float*>(reinterpret_cast<const char*>(vrow) + fb + ((fb >> 7) << 2));
+        if constexpr (PAD) vp = reinterpret_cast<const float*>(reinterpret_cast<const char*>(vrow) + fb + ((fb >> 7) << padsh));
 #pragma unroll
         for (int r = 0; r < RPT; r += 2) {
           const float2 q = __ffma2_rn(w2, make_float2(vp[r * VP], vp[(r + 1) * VP]), make_float2(h[r], h[r + 1]));
@@ -308,8 +315,9 @@ __device__ __forceinline__ void hphase_run_single(const float* __restrict__ Vs, 
 template <int RPT, int VW, bool GEN, bool PAD>
 __device__ __forceinline__ void hphase_run(const SParams& P, const float* Vs, const float2* Wp, const int4* pinfo, int64_t op_off,
                                            int npc, const HRole role, int gbase, int cnt) {
-  if (P.pairs) hphase_run_pairs<RPT, VW, GEN, PAD>(Vs, Wp, pinfo, P.out, op_off, P.epi, P.lout.stride_h, P.Ci, npc, role, gbase, cnt);
-  else hphase_run_single<RPT, VW, GEN, PAD>(Vs, reinterpret_cast<const float*>(Wp), pinfo, P.out, op_off, P.epi, P.lout.stride_h, P.Ci, npc, role, gbase, cnt);
+  const int padsh = P.pad == 4 ? 4 : P.pad == 2 ? 3 : 2;  // byte shift of (f >> 5) * q
+  if (P.pairs) hphase_run_pairs<RPT, VW, GEN, PAD>(Vs, Wp, pinfo, P.out, op_off, P.epi, P.lout.stride_h, P.Ci, npc, role, gbase, cnt, padsh);
+  else hphase_run_single<RPT, VW, GEN, PAD>(Vs, reinterpret_cast<const float*>(Wp), pinfo, P.out, op_off, P.epi, P.lout.stride_h, P.Ci, npc, role, gbase, cnt, padsh);
 }
 // bytes of the strip tables (after Vs) for a plan
 inline size_t strip_table_bytes(const SParams& P) {
@@ -371,14 +379,14 @@ inline int plan_stream(SParams& P, const StreamTables& T, int cap, int aln, int 
   for (int64_t a = 0; a < oW; a += strip_ox)
     for (int64_t o = a; o + 1 < std::min<int64_t>(oW, a + strip_ox); o += 2)
       shift = std::max<int>(shift, T.hw_start[o + 1] - T.hw_start[o]);
-  P.kp = P.Kw + shift;
   P.pairs = (int64_t)strip_ox * Ci >= 256 ? 1 : 0;  // enough independent items per row group to halve them
-  P.wtab_bytes = P.pairs ? (int)((size_t)((strip_ox + 1) / 2) * P.kp * sizeof(float2)) : (int)((size_t)strip_ox * P.Kw * sizeof(float));
+  P.kp = (P.pairs ? P.Kw + shift : P.Kw) | 1;
+  P.wtab_bytes = P.pairs ? (int)((size_t)((strip_ox + 1) / 2) * P.kp * sizeof(float2)) : (int)((size_t)strip_ox * P.kp * sizeof(float));
   if (P.kp >= (1 << 16) || (int64_t)((strip_ox + 1) / 2) * P.kp >= (1ll << 30)) return fail(AA_ERR_UNSUPPORTED, "stream: window too long");
   // Bank picture of the gather: the first 32 items of the first strip read, at tap 0, the columns below.
   // Pad the rows when that would at least halve a >= 4-way conflict.
   {
-    auto worst = [&](bool pad) {
+    auto worst = [&](int q) {
       int cnt[32] = {0}, w = 0;
       const int64_t f0 = ((int64_t)T.hw_start[0] * Ci) & ~(int64_t)(aln - 1);
       const int nitem = P.pairs ? (strip_ox + 1) / 2 * Ci : strip_ox * Ci;
@@ -386,13 +394,17 @@ inline int plan_stream(SParams& P, const StreamTables& T, int cap, int aln, int 
         const int o = P.pairs ? 2 * (l / Ci) : l / Ci, c = l % Ci;
         if (o >= oW) break;
         const int64_t f = (int64_t)T.hw_start[o] * Ci + c - f0;
-        const int64_t pos = pad ? f + (f >> 5) : f;
-        w = std::max(w, ++cnt[pos & 31]);
+        w = std::max(w, ++cnt[(f + (f >> 5) * q) & 31]);
       }
       return w;
     };
-    const int w0 = worst(false), w1 = worst(true);
-    P.pad = (w0 >= 4 && 2 * w1 <= w0) ? 1 : 0;
+    const int w0 = worst(0);
+    int best_q = 0, best_w = w0;
+    for (int q : {1, 2, 4}) {
+      const int w = worst(q);
+      if (w < best_w) { best_w = w; best_q = q; }
+    }
+    P.pad = (w0 >= 4 && 2 * best_w <= w0) ? best_q : 0;
   }
   P.tg = tg;
   P.vr = (P.tg - 1 + fmax + 3) / 4 * 4;
