@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(NT) aa_band_kernel(const BParams P) {
       const float* hr = P.h_w + (int64_t)oy * P.h_pitch;
 #pragma unroll
       for (int k = 0; k < KH; k++) rec[k] = k < sz ? __ldg(hr + k) : 0.f;
-      rec[KH] = __int_as_float((st - ra) * TXF);
+      rec[KH] = __int_as_float((sz > 0 ? st - ra : 0) * TXF);  // empty window: any initialised rows
     }
   };
   auto store_rec = [&](int c, const float (&rec)[HR * 4]) {
@@ -190,7 +190,9 @@ __global__ void __launch_bounds__(NT) aa_band_kernel(const BParams P) {
       const float* wr = P.w_w + (int64_t)ox * P.w_pitch;
 #pragma unroll
       for (int k = 0; k < KW; k++) w[k] = k < sz ? __ldg(wr + k) : 0.f;
-      soff = st * Ci + c - c0 + lead;
+      // an empty window (adjoint tables: a grad_in column no grad_out column reaches) starts past the patch: its
+      // taps all have zero weight, point them at loaded data
+      soff = sz > 0 ? st * Ci + c - c0 + lead : 0;
     } else {
 #pragma unroll
       for (int k = 0; k < KW; k++) w[k] = 0.f;

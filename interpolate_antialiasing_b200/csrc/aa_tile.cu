@@ -59,7 +59,9 @@ template <int KH, int VR> struct VRec {
   static constexpr int HR = (KH + 1 + 3) / 4;  // VR=1: float4 per row record {w[KH], first T row}
   static constexpr int U4 = KH + 3;            // VR=4: T rows a group of 4 output rows spans
   static constexpr int GR = U4 + 1;            // VR=4: float4 per group record {w quad per T row, first T row}
-  static constexpr int ZR = VR == 4 ? U4 - 1 : KH - 1;  // zero rows below the last window
+  // zero rows below the last window: what the unrolled tap loop can touch past it, + 1 so that a tile of empty
+  // windows only (adjoint tables) still reads initialised rows
+  static constexpr int ZR = (VR == 4 ? U4 - 1 : KH - 1) + 1;
   static __host__ __device__ constexpr int rec4(int ty) { return VR == 4 ? (ty / 4) * GR : ty * HR; }
 };
 
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
         const float* hr = P.h_w + (int64_t)oy * P.h_pitch;
 #pragma unroll
         for (int k = 0; k < KH; k++) rec[k] = k < sz ? __ldg(hr + k) : 0.f;
-        rec[KH] = __int_as_float((st - r0) * TXF);
+        rec[KH] = __int_as_float((sz > 0 ? st - r0 : 0) * TXF);  // empty window: any initialised rows
       }
 #pragma unroll
       for (int q = 0; q < HR; q++) hrec[tid * HR + q] = make_float4(rec[4 * q], rec[4 * q + 1], rec[4 * q + 2], rec[4 * q + 3]);
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
           for (int k = 0; k < KH; k++)
             if (k < sz) gw[4 * (d + k) + j] = __ldg(hr + k);
         }
-        if (j == 0) gw[4 * R::U4] = __int_as_float((base - r0) * TXF);
+        if (j == 0) gw[4 * R::U4] = __int_as_float((base - r0 < nr ? base - r0 : 0) * TXF);  // all-empty group: any initialised rows
       }
     }
   }
@@ -206,7 +208,9 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
       const float* wr = P.w_w + (int64_t)ox * P.w_pitch;
 #pragma unroll
       for (int k = 0; k < KW; k++) w[k] = k < sz ? __ldg(wr + k) : 0.f;
-      soff = st * Ci + c - c0 + lead;
+      // an empty window (adjoint tables: a grad_in column no grad_out column reaches) starts past the patch: its
+      // taps all have zero weight, point them at loaded data
+      soff = sz > 0 ? st * Ci + c - c0 + lead : 0;
     } else {
 #pragma unroll
       for (int k = 0; k < KW; k++) w[k] = 0.f;

@@ -178,3 +178,32 @@ def test_backward_of_upsampling_on_streaming_kernel(cuda):
                     ran += flags == capi.FLAG_FORCE_STREAM
                     np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-4)
     assert ran >= 12
+
+
+def test_backward_with_uncovered_rows_and_columns(cuda):
+    """align_corners with a 1-pixel output axis (scale 0: only input index 0 contributes) and the box filter leave
+    grad_input rows / columns that NO grad_output element reaches: empty adjoint windows.  Their gathers must read
+    initialised memory only (found by the fuzz: a zero weight times stale NaNs in shared memory).  Shared memory is
+    pre-loaded with NaNs by resizing an all-NaN tensor through the same kernels right before every case."""
+    from interpolate_antialiasing_b200 import capi
+    g = torch.Generator().manual_seed(29)
+    poison_f = torch.full((2, 5, 160, 64), float("nan"), device=cuda)
+    poison_b = torch.full((2, 5, 40, 16), float("nan"), device=cuda)
+    cases = [((2, 5, 145, 12), (145, 1)), ((2, 5, 12, 145), (1, 145)), ((1, 3, 33, 40), (1, 1)), ((1, 2, 300, 7), (5, 1)),
+             ((2, 1, 64, 64), (1, 16)), ((1, 4, 9, 300), (1, 2))]
+    for shp, osz in cases:
+        for mode in ("linear", "cubic", "nearest"):
+            for cl in (False, True):
+                go = torch.rand(shp[:2] + osz, generator=g)
+                want = O.backward_adjoint(go.numpy(), shp, mode, True)
+                gc = go.to(cuda)
+                if cl:
+                    gc = gc.contiguous(memory_format=torch.channels_last)
+                for _ in range(2):
+                    capi.resize_forward(poison_f, (120, 48), mode, False)          # band / tile kernels, NaN patches
+                    capi.resize_backward(poison_b, (2, 5, 160, 64), mode, False)   # tile kernel (adjoint), NaN patches
+                    got = capi.resize_backward(gc, shp, mode, True)
+                    torch.cuda.synchronize()
+                    a = got.cpu().numpy()
+                    assert np.isfinite(a).all(), (shp, osz, mode, cl)
+                    np.testing.assert_allclose(a, want, rtol=1e-5, atol=1e-4)
