@@ -166,6 +166,13 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
         for (int q = 0; q < RS4; q++) rq[i][q] = __ldg(rp + i * RS4 + q);
       ip += U * stride_h;
       rp += U * RS4;
+      // next batch -> L2 while this one is consumed, and across the horizontal phase, when no load of this CTA is
+      // in flight: a hint, no registers (measured +3..7 points of HBM peak wherever the horizontal phase is a
+      // large share: scales 0.125x-0.5x, bicubic, backward of upsampling; neutral on cfg2)
+      if (y + 2 * U <= yB) {
+#pragma unroll
+        for (int i = 0; i < U; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(ip + i * stride_h));
+      }
 #pragma unroll
       for (int i = 0; i < U; i++) row(v[i], rq[i]);
       if (cnt >= P.tg) hphase();
