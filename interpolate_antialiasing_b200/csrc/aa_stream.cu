@@ -45,7 +45,7 @@ namespace {
 // MINB  CTAs per SM the register allocation must allow
 // Shared memory holds up to P.vr vertically-filtered rows; the horizontal phase runs at the end of a
 // U-row batch once at least P.tg rows are buffered (host guarantees tg - 1 + max flushes per batch <= vr).
-template <int A, int VEC, typename in_t, int NT, int U, int MINB, bool GEN, bool PAD>
+template <int A, int VEC, typename in_t, int NT, int U, int MINB, bool GEN, bool PAD, bool PF = true>
 __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
   extern __shared__ __align__(16) float smem[];
   constexpr int RPT = 4;
@@ -166,16 +166,23 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
         for (int q = 0; q < RS4; q++) rq[i][q] = __ldg(rp + i * RS4 + q);
       ip += U * stride_h;
       rp += U * RS4;
-      // next batch -> L2 while this one is consumed, and across the horizontal phase, when no load of this CTA is
-      // in flight: a hint, no registers (measured +3..7 points of HBM peak wherever the horizontal phase is a
-      // large share: scales 0.125x-0.5x, bicubic, uint8, backward of upsampling; same-box A/B on cfg2: channels_first
-      // +0.8 %, channels_last -1.7 %)
-      if (y + 2 * U <= yB) {
+      // L2 prefetch of a later batch: keeps HBM busy across the horizontal phase, when no load of this CTA is in
+      // flight -- a hint, no registers (measured +3..7 points of HBM peak wherever the horizontal phase is a large
+      // share: scales 0.125x-0.5x, bicubic, uint8, backward of upsampling).  Where the hints are issued is chosen
+      // per shape by what ptxas then does with the real loads (scripts/sass_lint.py): for the 3-accumulator
+      // shapes at the END of the batch (the batch after the next one), so that they do not queue ahead of this
+      // batch's loads; for the others next to the loads (the next batch).
+      constexpr bool PF_AT_END = A * VEC <= 12;
+      if (PF && !PF_AT_END && y + 2 * U <= yB) {
 #pragma unroll
         for (int i = 0; i < U; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(ip + i * stride_h));
       }
 #pragma unroll
       for (int i = 0; i < U; i++) row(v[i], rq[i]);
+      if (PF && PF_AT_END && y + 3 * U <= yB) {
+#pragma unroll
+        for (int i = 0; i < U; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(ip + (U + i) * stride_h));
+      }
       if (cnt >= P.tg) hphase();
     }
     for (; y < yB; y++) {
@@ -237,6 +244,9 @@ int launch_cfg(SParams& P, const StreamTables& T, int device, cudaStream_t strea
       }
     }
     if (!P.pad) {
+      if constexpr (!GEN && NT_ == 256 && VEC == 4 && sizeof(in_t) == 4)  // the variant without L2 hints (see below)
+        AA_CUDA_TRY(cudaFuncSetAttribute(aa_stream_kernel<A, VEC, in_t, C::NT, C::U, C::MINB, GEN, false, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       AA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NT, smem_));
     }
@@ -258,6 +268,16 @@ int launch_cfg(SParams& P, const StreamTables& T, int device, cudaStream_t strea
     if (P.pad) {
       using CP = Cfg<A, VEC, in_t, NT_, true>;
       aa_stream_kernel<A, VEC, in_t, CP::NT, CP::U, CP::MINB, GEN, true><<<(unsigned)grid, C::NT, smem, stream>>>(P);
+      AA_LAUNCH_CHECK("aa_stream_kernel");
+      return AA_OK;
+    }
+  }
+  // Long uninterrupted streams (fewer than 1 output pixel per 32 input pixels, e.g. cfg2: the horizontal phase is a
+  // few percent of the CTA's time) run the variant without the L2 hints: there the hints buy nothing and the kernel
+  // with them measured 2 % slower on channels_last cfg2 (same-box A/B).
+  if constexpr (!GEN && NT_ == 256 && VEC == 4 && sizeof(in_t) == 4) {
+    if (!P.pad && P.oH * P.oW * 32 < P.H * T.n_in_w) {
+      aa_stream_kernel<A, VEC, in_t, C::NT, C::U, C::MINB, GEN, false, false><<<(unsigned)grid, C::NT, smem, stream>>>(P);
       AA_LAUNCH_CHECK("aa_stream_kernel");
       return AA_OK;
     }

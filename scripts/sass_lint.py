@@ -15,9 +15,9 @@ for line in out.splitlines():
         funcs[cur].append(line.split("*/", 1)[1].strip())
 bad = 0
 for name, ins in funcs.items():
-    k = re.search(r"aa_stream_kernelILi(\d+)ELi(\d+)E(\w)Li(\d+)ELi(\d+)ELi(\d+)ELb(\d)ELb(\d)", name)
+    k = re.search(r"aa_stream_kernelILi(\d+)ELi(\d+)E(\w)Li(\d+)ELi(\d+)ELi(\d+)ELb(\d)ELb(\d)ELb(\d)", name)
     if not k: continue
-    A, VEC, ty, NT, U, MINB, GEN, PAD = k.groups()
+    A, VEC, ty, NT, U, MINB, GEN, PAD, PF = k.groups()
     U = int(U)
     # runs of wide data loads (the .NA = no-allocate data rows) between FFMA2s
     best, run = 0, 0
@@ -27,5 +27,5 @@ for name, ins in funcs.items():
             best = max(best, run); run = 0
     flag = "" if best >= U else "   <-- loads not hoisted"
     bad += best < U
-    print(f"A={A} VEC={VEC} {ty} NT={NT} U={U} GEN={GEN} PAD={PAD}: {best} data loads before the first FMA{flag}")
+    print(f"A={A} VEC={VEC} {ty} NT={NT} U={U} GEN={GEN} PAD={PAD} PF={PF}: {best} data loads before the first FMA{flag}")
 print("flagged:", bad)

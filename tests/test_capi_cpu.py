@@ -105,4 +105,5 @@ def test_stream_kernels_issue_row_loads_before_first_fma():
     assert r.returncode == 0, r.stderr[-2000:]
     flagged = [l for l in r.stdout.splitlines() if "<--" in l]
     assert flagged and all(l.startswith("A=6 VEC=8 h") for l in flagged) or not flagged, "\n".join(flagged)
-    assert any(l.startswith("A=3 VEC=4 f NT=256 U=4 GEN=0 PAD=0: 4 data loads") for l in r.stdout.splitlines())
+    assert any(l.startswith("A=3 VEC=4 f NT=256 U=4 GEN=0 PAD=0 PF=0: 4 data loads") for l in r.stdout.splitlines())
+    assert any(l.startswith("A=3 VEC=4 f NT=256 U=4 GEN=0 PAD=0 PF=1: 4 data loads") for l in r.stdout.splitlines())
