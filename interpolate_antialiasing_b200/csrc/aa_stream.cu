@@ -244,7 +244,7 @@ int launch_cfg(SParams& P, const StreamTables& T, int device, cudaStream_t strea
       }
     }
     if (!P.pad) {
-      if constexpr (!GEN && NT_ == 256 && VEC == 4 && sizeof(in_t) == 4)  // the variant without L2 hints (see below)
+      if constexpr (A == 3 && !GEN && NT_ == 256 && VEC == 4 && sizeof(in_t) == 4)  // the variant without L2 hints (see below)
         AA_CUDA_TRY(cudaFuncSetAttribute(aa_stream_kernel<A, VEC, in_t, C::NT, C::U, C::MINB, GEN, false, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -272,10 +272,11 @@ int launch_cfg(SParams& P, const StreamTables& T, int device, cudaStream_t strea
       return AA_OK;
     }
   }
-  // Long uninterrupted streams (fewer than 1 output pixel per 32 input pixels, e.g. cfg2: the horizontal phase is a
-  // few percent of the CTA's time) run the variant without the L2 hints: there the hints buy nothing and the kernel
-  // with them measured 2 % slower on channels_last cfg2 (same-box A/B).
-  if constexpr (!GEN && NT_ == 256 && VEC == 4 && sizeof(in_t) == 4) {
+  // Long uninterrupted bilinear streams (3 accumulators, fewer than 1 output pixel per 32 input pixels, e.g. cfg2: the
+  // horizontal phase is a few percent of the CTA's time) run the variant without the L2 hints: there the hints buy
+  // little and the kernel with them measured 2 % slower on channels_last cfg2 (same-box A/B).  The bicubic shapes
+  // gain from the hints at every scale.
+  if constexpr (A == 3 && !GEN && NT_ == 256 && VEC == 4 && sizeof(in_t) == 4) {
     if (!P.pad && P.oH * P.oW * 32 < P.H * T.n_in_w) {
       aa_stream_kernel<A, VEC, in_t, C::NT, C::U, C::MINB, GEN, false, false><<<(unsigned)grid, C::NT, smem, stream>>>(P);
       AA_LAUNCH_CHECK("aa_stream_kernel");
