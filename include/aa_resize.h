@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define AA_RESIZE_ABI_VERSION 1
+#define AA_RESIZE_ABI_VERSION 2
 
 typedef enum aa_status {
   AA_OK = 0,
@@ -60,6 +60,9 @@ typedef enum aa_dtype {
                                     shape/layout is not eligible)                                   */
 #define AA_FLAG_STREAM_TMA 4u    /* streaming kernel: stage input rows with cp.async.bulk (TMA)     */
 #define AA_FLAG_STREAM_LDG 8u    /* streaming kernel: plain vectorised global loads, single role    */
+#define AA_FLAG_VMMA 64u         /* uint8 input: vertical pass on the tensor cores (tcgen05 kind::i8 + TMA, aa_vmma.cu);
+                                    fails with AA_ERR_UNSUPPORTED if not eligible.  AUTO picks it for uint8 inputs
+                                    downsampled >= 2x vertically                                      */
 #define AA_FLAG_ROUND_NEAREST 32u /* uint8 output: round to nearest (PIL) instead of truncating (.byte()) */
 
 /* A 4-D tensor view [n, c, h, w] with ELEMENT strides, resident on CUDA device `device`.
@@ -94,6 +97,13 @@ const char* aa_last_error(void);
 int aa_interp_size(int64_t in_size, int64_t out_size, int filter, int align_corners, int dtype,
                    int32_t* interp_size_out);
 
+/* The integer window tables of one axis computed ON THE HOST with the same IEEE operations as the table kernel
+ * (what the library's launch planning uses instead of reading the device tables back).  xmin/xsize: [out_size] host
+ * arrays; scale_factor <= 0 means "not given".  Same reference lines as aa_build_tables (:253-257); bit-identical to
+ * it and to the oracle (tests/test_capi_cpu.py, tests/test_tables_gpu.py). */
+int aa_host_tables(int64_t in_size, int64_t out_size, int filter, int align_corners, int dtype, double scale_factor,
+                   int64_t* xmin, int64_t* xsize);
+
 /* ---- tables -------------------------------------------------------------------------------- */
 
 /* Builds one axis' tables with the sm_100a table kernel and copies them, in the reference's
@@ -102,6 +112,9 @@ int aa_interp_size(int64_t in_size, int64_t out_size, int filter, int align_corn
  * :337-363, :379-405 (+ :194-281).  Integer tables and weights are bit-exact. */
 int aa_build_tables(int64_t in_size, int64_t out_size, int filter, int align_corners, int dtype,
                     int device, aa_tables_desc* dst, void* cuda_stream);
+/* same with a caller-provided scale factor for the axis (see aa_scales below; <= 0: not given) */
+int aa_build_tables_sf(int64_t in_size, int64_t out_size, int filter, int align_corners, int dtype, double scale_factor,
+                       int device, aa_tables_desc* dst, void* cuda_stream);
 
 /* Pre-populates the table cache for a forward and/or backward call (so that the real calls never
  * synchronise, e.g. under CUDA-graph capture). */
@@ -110,6 +123,12 @@ int aa_warm_tables(int64_t in_h, int64_t in_w, int64_t out_h, int64_t out_w, int
 
 /* Drops every cached table on every device (frees device memory). */
 int aa_clear_table_cache(void);
+
+/* Health query for asynchronous failures that cannot surface through a return code: the persistent
+ * tensor-core kernel bounds every mbarrier wait and records a watchdog code instead of hanging the GPU.
+ * Call after synchronising the stream (one 4-byte D2H copy); AA_ERR_CUDA + message when a watchdog fired since
+ * the last call.  No reference counterpart (the reference is synchronous CPU code). */
+int aa_check_device(int device);
 
 /* ---- the hot path --------------------------------------------------------------------------- */
 
@@ -137,6 +156,20 @@ typedef struct aa_epilogue {
 } aa_epilogue;
 int aa_resize_forward_ex(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align_corners,
                          uint32_t flags, const aa_epilogue* epilogue, void* cuda_stream);
+
+/* Caller-provided scale factors: the `scale_factors` argument of ti_upsample_*2d_cpu
+ * (aa_interpolation_impl.h:735,740-742: get_scale_value -> area_pixel_compute_scale).  A value > 0 replaces the
+ * table scale in/out of that axis by 1/scale_factor (torch's interpolate(scale_factor=s, recompute_scale_factor=False));
+ * <= 0 or a null pointer means "not given" (what the reference's shim always passes, extension_interpolate.cpp:12).
+ * Ignored when align_corners is set, exactly like area_pixel_compute_scale. */
+typedef struct aa_scales {
+  double scale_h;
+  double scale_w;
+} aa_scales;
+int aa_resize_forward_sf(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align_corners,
+                         const aa_scales* scales, uint32_t flags, void* cuda_stream);
+int aa_resize_backward_sf(const aa_tensor_desc* grad_out, const aa_tensor_desc* grad_in, int filter, int align_corners,
+                          const aa_scales* scales, uint32_t flags, void* cuda_stream);
 
 /* grad_in = Wh^T * grad_out * Ww : the true adjoint of aa_resize_forward, gather form, no atomics,
  * no zero-fill pass.  Replaces ti_upsample_bilinear2d_backward_cpu,

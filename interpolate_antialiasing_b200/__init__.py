@@ -40,28 +40,38 @@ def load():
     return _ext
 
 
-def linear_forward(input, output_size, align_corners=False):
-    return load().linear_forward(input, list(output_size), align_corners)
+def _sz(v):
+    return None if v is None else [int(t) for t in v]
 
 
-def cubic_forward(input, output_size, align_corners=False):
-    return load().cubic_forward(input, list(output_size), align_corners)
+def _sf(v):
+    return None if v is None else [float(t) for t in v]
 
 
-def nearest_forward(input, output_size, align_corners=False):
-    return load().nearest_forward(input, list(output_size), align_corners)
+# `scale_factors` is the optional argument of the reference's ti_upsample_*2d_cpu (aa_interpolation_impl.h:735) that its
+# shim always leaves empty; with it output_size may be None (floor(in * scale)) and the table scale is 1/scale_factor.
+def linear_forward(input, output_size, align_corners=False, scale_factors=None):
+    return load().linear_forward(input, _sz(output_size), align_corners, _sf(scale_factors))
 
 
-def linear_backward(grad_output, output_size, input_size, align_corners=False):
-    return load().linear_backward(grad_output, list(output_size), list(input_size), align_corners)
+def cubic_forward(input, output_size, align_corners=False, scale_factors=None):
+    return load().cubic_forward(input, _sz(output_size), align_corners, _sf(scale_factors))
 
 
-def cubic_backward(grad_output, output_size, input_size, align_corners=False):
-    return load().cubic_backward(grad_output, list(output_size), list(input_size), align_corners)
+def nearest_forward(input, output_size, align_corners=False, scale_factors=None):
+    return load().nearest_forward(input, _sz(output_size), align_corners, _sf(scale_factors))
 
 
-def nearest_backward(grad_output, output_size, input_size, align_corners=False):
-    return load().nearest_backward(grad_output, list(output_size), list(input_size), align_corners)
+def linear_backward(grad_output, output_size, input_size, align_corners=False, scale_factors=None):
+    return load().linear_backward(grad_output, _sz(output_size), list(input_size), align_corners, _sf(scale_factors))
+
+
+def cubic_backward(grad_output, output_size, input_size, align_corners=False, scale_factors=None):
+    return load().cubic_backward(grad_output, _sz(output_size), list(input_size), align_corners, _sf(scale_factors))
+
+
+def nearest_backward(grad_output, output_size, input_size, align_corners=False, scale_factors=None):
+    return load().nearest_backward(grad_output, _sz(output_size), list(input_size), align_corners, _sf(scale_factors))
 
 
 def linear_backward_nonaa(grad_output, output_size, input_size, align_corners=False):

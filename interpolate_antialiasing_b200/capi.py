@@ -12,11 +12,12 @@ from ._build_ext import LIB
 BOX, TRIANGLE, CUBIC = 0, 1, 2
 U8, F32, F64, F16, BF16 = 0, 1, 2, 3, 4
 FLAG_AUTO, FLAG_FORCE_GENERAL, FLAG_FORCE_STREAM, FLAG_STREAM_TMA, FLAG_STREAM_LDG, FLAG_ROUND_NEAREST = 0, 1, 2, 4, 8, 32
+FLAG_VMMA = 64
 FILTERS = {"nearest": BOX, "box": BOX, "bilinear": TRIANGLE, "linear": TRIANGLE, "bicubic": CUBIC, "cubic": CUBIC}
 
 EXPORTS = [
-    "aa_abi_version", "aa_last_error", "aa_interp_size", "aa_build_tables", "aa_warm_tables",
-    "aa_clear_table_cache", "aa_resize_forward", "aa_resize_forward_ex", "aa_resize_backward",
+    "aa_abi_version", "aa_last_error", "aa_interp_size", "aa_host_tables", "aa_build_tables", "aa_build_tables_sf", "aa_warm_tables",
+    "aa_clear_table_cache", "aa_check_device", "aa_resize_forward", "aa_resize_forward_sf", "aa_resize_backward_sf", "aa_resize_forward_ex", "aa_resize_backward",
     "aa_resize_backward_nonaa_bilinear", "aa_resize_forward_host", "aa_launch_count",
 ]
 
@@ -35,6 +36,10 @@ class TablesDesc(ctypes.Structure):
 
 class Epilogue(ctypes.Structure):
     _fields_ = [("normalize", ctypes.c_int32), ("scale", ctypes.c_float * 4), ("bias", ctypes.c_float * 4)]
+
+
+class Scales(ctypes.Structure):
+    _fields_ = [("scale_h", ctypes.c_double), ("scale_w", ctypes.c_double)]
 
 
 class AAError(RuntimeError):
@@ -58,12 +63,17 @@ def lib():
         L.aa_last_error.restype = ctypes.c_char_p
         L.aa_interp_size.argtypes = [i64, i64, i32, i32, i32, P(i32)]
         L.aa_build_tables.argtypes = [i64, i64, i32, i32, i32, i32, P(TablesDesc), vp]
+        L.aa_build_tables_sf.argtypes = [i64, i64, i32, i32, i32, ctypes.c_double, i32, P(TablesDesc), vp]
+        L.aa_host_tables.argtypes = [i64, i64, i32, i32, i32, ctypes.c_double, vp, vp]
         L.aa_warm_tables.argtypes = [i64, i64, i64, i64, i32, i32, i32, i32, vp]
         L.aa_resize_forward.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, u32, vp]
+        L.aa_resize_forward_sf.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, P(Scales), u32, vp]
+        L.aa_resize_backward_sf.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, P(Scales), u32, vp]
         L.aa_resize_forward_ex.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, u32, P(Epilogue), vp]
         L.aa_resize_backward.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, u32, vp]
         L.aa_resize_backward_nonaa_bilinear.argtypes = [P(TensorDesc), P(TensorDesc), i32, vp]
         L.aa_resize_forward_host.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, u32]
+        L.aa_check_device.argtypes = [i32]
         L.aa_launch_count.argtypes = [i32]
         L.aa_launch_count.restype = i64
         _lib = L
@@ -102,27 +112,45 @@ def interp_size(in_size, out_size, filter, align_corners=False, dtype=F32):
     return k.value
 
 
-def build_tables(in_size, out_size, filter, align_corners=False, dtype=None, device=0):
+def host_tables(in_size, out_size, filter, align_corners=False, dtype=F32, scale=None):
+    """-> (xmin, xsize) int64 numpy arrays computed on the host (no device): the launch planners' view of the tables."""
+    import numpy as np
+    xmin = np.empty(out_size, np.int64)
+    xsize = np.empty(out_size, np.int64)
+    check(lib().aa_host_tables(in_size, out_size, _filter(filter), int(align_corners), dtype, float(scale or 0.0),
+                               xmin.ctypes.data, xsize.ctypes.data))
+    return xmin, xsize
+
+
+def build_tables(in_size, out_size, filter, align_corners=False, dtype=None, device=0, scale=None):
     """-> (xmin int64[out], xsize int64[out], weights [out, K]) as CUDA tensors, built by the table kernel."""
     import torch
     dtype = dtype or torch.float32
     code = F64 if dtype == torch.float64 else F32
-    K = interp_size(in_size, out_size, filter, align_corners, code)
+    if scale and not align_corners:
+        import numpy as np  # K = ceil(support)*2+1 with support from the caller's scale (aa_interpolation_impl.h:208-210)
+        sc = np.float32(1.0 / scale) if code == F32 else np.float64(1.0 / scale)
+        base = {BOX: 0.5, TRIANGLE: 1.0, CUBIC: 2.0}[_filter(filter)]
+        sup = (np.float32(base * np.float64(sc)) if code == F32 else base * sc) if sc >= 1.0 else base
+        K = int(np.ceil(np.float32(sup))) * 2 + 1
+    else:
+        K = interp_size(in_size, out_size, filter, align_corners, code)
     dev = torch.device("cuda", device)
     xmin = torch.empty(out_size, dtype=torch.int64, device=dev)
     xsize = torch.empty(out_size, dtype=torch.int64, device=dev)
     w = torch.empty((out_size, K), dtype=dtype, device=dev)
     td = TablesDesc(xmin.data_ptr(), xsize.data_ptr(), w.data_ptr(), 0)
     with torch.cuda.device(dev):
-        check(lib().aa_build_tables(in_size, out_size, _filter(filter), int(align_corners), code, device,
-                                    ctypes.byref(td), _stream(xmin)))
+        check(lib().aa_build_tables_sf(in_size, out_size, _filter(filter), int(align_corners), code, float(scale or 0.0),
+                                       device, ctypes.byref(td), _stream(xmin)))
     assert td.interp_size == K
     return xmin, xsize, w
 
 
-def resize_forward(x, output_size, filter, align_corners=False, flags=FLAG_AUTO, out=None, out_u8=False):
+def resize_forward(x, output_size, filter, align_corners=False, flags=FLAG_AUTO, out=None, out_u8=False, scales=None):
     """C-ABI forward on a CUDA tensor already contiguous in channels_first or channels_last.
-    out_u8=True allocates a uint8 output: the clamp + truncate/round epilogue is fused (FLAG_ROUND_NEAREST)."""
+    out_u8=True allocates a uint8 output: the clamp + truncate/round epilogue is fused (FLAG_ROUND_NEAREST).
+    scales=(sh, sw): the reference's `scale_factors` (aa_resize_forward_sf)."""
     import torch
     N, C, H, W = x.shape
     oH, oW = int(output_size[0]), int(output_size[1])
@@ -131,7 +159,12 @@ def resize_forward(x, output_size, filter, align_corners=False, flags=FLAG_AUTO,
         out = torch.empty((N, C, oH, oW), dtype=torch.uint8 if out_u8 else (torch.float64 if x.dtype == torch.float64 else torch.float32),
                           device=x.device, memory_format=torch.channels_last if cl else torch.contiguous_format)
     di, do = desc(x), desc(out)
-    check(lib().aa_resize_forward(ctypes.byref(di), ctypes.byref(do), _filter(filter), int(align_corners), flags, _stream(x)))
+    if scales is not None:
+        sc = Scales(float(scales[0] or 0.0), float(scales[1] or 0.0))
+        check(lib().aa_resize_forward_sf(ctypes.byref(di), ctypes.byref(do), _filter(filter), int(align_corners),
+                                         ctypes.byref(sc), flags, _stream(x)))
+    else:
+        check(lib().aa_resize_forward(ctypes.byref(di), ctypes.byref(do), _filter(filter), int(align_corners), flags, _stream(x)))
     return out
 
 
@@ -149,13 +182,17 @@ def resize_forward_ex(x, output_size, filter, out, scale=None, bias=None, align_
     return out
 
 
-def resize_backward(grad_out, input_size, filter, align_corners=False, nonaa=False, flags=FLAG_AUTO):
+def resize_backward(grad_out, input_size, filter, align_corners=False, nonaa=False, flags=FLAG_AUTO, scales=None):
     import torch
     cl = grad_out.is_contiguous(memory_format=torch.channels_last) and not grad_out.is_contiguous()
     gin = torch.empty(tuple(input_size), dtype=grad_out.dtype, device=grad_out.device,
                       memory_format=torch.channels_last if cl else torch.contiguous_format)
     dg, di = desc(grad_out), desc(gin)
-    if nonaa:
+    if scales is not None:
+        sc = Scales(float(scales[0] or 0.0), float(scales[1] or 0.0))
+        check(lib().aa_resize_backward_sf(ctypes.byref(dg), ctypes.byref(di), _filter(filter), int(align_corners),
+                                          ctypes.byref(sc), flags, _stream(grad_out)))
+    elif nonaa:
         check(lib().aa_resize_backward_nonaa_bilinear(ctypes.byref(dg), ctypes.byref(di), int(align_corners), _stream(grad_out)))
     else:
         check(lib().aa_resize_backward(ctypes.byref(dg), ctypes.byref(di), _filter(filter), int(align_corners), flags, _stream(grad_out)))
@@ -167,6 +204,11 @@ def resize_forward_host(x_host, out_host, filter, align_corners=False, flags=FLA
     di, do = desc(x_host, device), desc(out_host, device)
     check(lib().aa_resize_forward_host(ctypes.byref(di), ctypes.byref(do), _filter(filter), int(align_corners), flags))
     return out_host
+
+
+def check_device(device=0):
+    """Raises if a kernel watchdog fired on `device` since the last call (call after torch.cuda.synchronize())."""
+    check(lib().aa_check_device(device))
 
 
 def launch_count(reset=False):

@@ -75,8 +75,22 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-BandedAxis fwd_axis(const AxisTables* t) { return BandedAxis{t->xmin, t->xsize, t->w, t->K, t->in, t->out, t->h_xmin.data(), t->h_xsize.data()}; }
-BandedAxis adj_axis(const AxisTables* t) { return BandedAxis{t->omin, t->osize, t->wT, t->KT, t->out, t->in, t->h_omin.data(), t->h_osize.data()}; }
+BandedAxis fwd_axis(const AxisTables* t) {
+  return BandedAxis{t->xmin, t->xsize, t->w, t->K, t->in, t->out, t->h_xmin.data(), t->h_xsize.data(), t->id * 2, t->device};
+}
+BandedAxis adj_axis(const AxisTables* t) {
+  return BandedAxis{t->omin, t->osize, t->wT, t->KT, t->out, t->in, t->h_omin.data(), t->h_osize.data(), t->id * 2 + 1, t->device};
+}
+
+// AUTO policy for the tensor-core path: vertical downsampling with enough taps that the FP32-pipe kernel is
+// instruction-bound (measured crossover).  AA_VMMA_AUTO=0 disables, =1 forces wherever eligible.
+bool vmma_auto(const AxisTables* th, const AxisTables* tw) {
+  static const int mode = [] { const char* e = getenv("AA_VMMA_AUTO"); return e ? atoi(e) : -1; }();
+  if (mode == 0) return false;
+  if (mode == 1) return true;
+  (void)tw;
+  return th->scale_f >= 2.0f && th->xsize_max >= 5;
+}
 
 __global__ void widen_i32_i64(const int32_t* __restrict__ a, int64_t* __restrict__ b, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,7 +98,7 @@ __global__ void widen_i32_i64(const int32_t* __restrict__ a, int64_t* __restrict
 }
 
 int forward_impl(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align, uint32_t flags,
-                 cudaStream_t stream, const aa_epilogue* ex = nullptr) {
+                 cudaStream_t stream, const aa_epilogue* ex = nullptr, const aa_scales* sc = nullptr) {
   int rc;
   if ((rc = check_desc(in, "input")) != AA_OK) return rc;
   if ((rc = check_desc(out, "output")) != AA_OK) return rc;
@@ -133,13 +147,13 @@ int forward_impl(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter
   DeviceGuard g(in->device);
   if (!g.ok) return cuda_fail(g.err, "cudaSetDevice");
   std::shared_ptr<AxisTables> th, tw;
-  if ((rc = get_axis_tables(in->device, in->h, out->h, filter, align, tdtype, stream, &th)) != AA_OK) return rc;
-  if ((rc = get_axis_tables(in->device, in->w, out->w, filter, align, tdtype, stream, &tw)) != AA_OK) return rc;
+  if ((rc = get_axis_tables(in->device, in->h, out->h, filter, align, tdtype, sc ? sc->scale_h : 0.0, stream, &th)) != AA_OK) return rc;
+  if ((rc = get_axis_tables(in->device, in->w, out->w, filter, align, tdtype, sc ? sc->scale_w : 0.0, stream, &tw)) != AA_OK) return rc;
   if (!(flags & AA_FLAG_FORCE_GENERAL) && tdtype == AA_F32) {
     // few taps on both axes (near scale 1 / upsampling): output-bound -> tile kernel;
     // otherwise (downsampling): input-bound -> streaming kernel.
     const bool few_taps = th->xsize_max <= 7 && tw->xsize_max <= 7;
-    if (few_taps && !(flags & AA_FLAG_FORCE_STREAM)) {
+    if (few_taps && !(flags & (AA_FLAG_FORCE_STREAM | AA_FLAG_VMMA))) {
       // mild vertical downsampling (1x..1.6x fewer rows): the band-walking variant; otherwise one tile per CTA
       if (out->h <= in->h && in->h * 5 <= out->h * 8) {
         rc = launch_band(in->data, in->dtype, lin, out->data, lout, fwd_axis(th.get()), fwd_axis(tw.get()), th->xsize_max,
@@ -149,6 +163,12 @@ int forward_impl(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter
       rc = launch_tile(in->data, in->dtype, lin, out->data, lout, fwd_axis(th.get()), fwd_axis(tw.get()), th->xsize_max,
                        tw->xsize_max, epi, stream);
       if (rc != AA_ERR_UNSUPPORTED) return rc;
+    }
+    // uint8 pixels, many vertical taps: vertical pass on the tensor cores (aa_vmma.cu)
+    if (in->dtype == AA_U8 && !(flags & (AA_FLAG_FORCE_STREAM | AA_FLAG_STREAM_TMA | AA_FLAG_STREAM_LDG)) &&
+        ((flags & AA_FLAG_VMMA) || vmma_auto(th.get(), tw.get()))) {
+      rc = launch_vmma(in->data, lin, out->data, lout, th.get(), tw.get(), in->h, in->w, out->h, out->w, epi, stream);
+      if (rc != AA_ERR_UNSUPPORTED || (flags & AA_FLAG_VMMA)) return rc;
     }
     rc = launch_stream(in->data, in->dtype, lin, out->data, lout, th.get(), tw.get(), in->h, in->w, out->h, out->w,
                        flags, epi, stream);
@@ -167,7 +187,8 @@ int backward_check(const aa_tensor_desc* gout, const aa_tensor_desc* gin, Layout
   if ((rc = check_desc(gin, "grad_input")) != AA_OK) return rc;
   if (gout->n != gin->n || gout->c != gin->c) return fail(AA_ERR_INVALID, "grad_output and grad_input must agree in n and c");
   if (gout->device != gin->device) return fail(AA_ERR_INVALID, "grad tensors must live on the same device");
-  if (gout->dtype == AA_U8 || gout->dtype != gin->dtype) return fail(AA_ERR_INVALID, "backward: f32 or f64, same dtype on both sides");
+  if ((gout->dtype != AA_F32 && gout->dtype != AA_F64) || gout->dtype != gin->dtype)
+    return fail(AA_ERR_INVALID, "backward: f32 or f64, same dtype on both sides");
   bool o_cl = false, i_cl = false;
   if ((rc = classify_layout(*gout, false, lo, &o_cl)) != AA_OK) return rc;
   if ((rc = classify_layout(*gin, o_cl, li, &i_cl)) != AA_OK) return rc;
@@ -202,8 +223,26 @@ int aa_interp_size(int64_t in_size, int64_t out_size, int filter, int align_corn
   return AA_OK;
 }
 
+int aa_host_tables(int64_t in_size, int64_t out_size, int filter, int align_corners, int dtype, double scale_factor,
+                   int64_t* xmin, int64_t* xsize) {
+  int rc;
+  if ((rc = check_filter(filter)) != AA_OK) return rc;
+  if (!xmin || !xsize || in_size <= 0 || out_size <= 0 || in_size >= (1ll << 31) || out_size >= (1ll << 31))
+    return fail(AA_ERR_INVALID, "aa_host_tables: bad arguments");
+  std::vector<int32_t> a((size_t)out_size), b((size_t)out_size);
+  host_int_tables(in_size, out_size, filter, align_corners ? 1 : 0, dtype == AA_F64 ? AA_F64 : AA_F32,
+                  (align_corners || !(scale_factor > 0.0)) ? 0.0 : scale_factor, a.data(), b.data());
+  for (int64_t i = 0; i < out_size; i++) { xmin[i] = a[(size_t)i]; xsize[i] = b[(size_t)i]; }
+  return AA_OK;
+}
+
 int aa_build_tables(int64_t in_size, int64_t out_size, int filter, int align_corners, int dtype, int device,
                     aa_tables_desc* dst, void* cuda_stream) {
+  return aa_build_tables_sf(in_size, out_size, filter, align_corners, dtype, 0.0, device, dst, cuda_stream);
+}
+
+int aa_build_tables_sf(int64_t in_size, int64_t out_size, int filter, int align_corners, int dtype, double scale_factor,
+                       int device, aa_tables_desc* dst, void* cuda_stream) {
   int rc;
   if ((rc = check_filter(filter)) != AA_OK) return rc;
   if (!dst || !dst->xmin || !dst->xsize || !dst->weights) return fail(AA_ERR_INVALID, "aa_build_tables: null destination");
@@ -212,7 +251,7 @@ int aa_build_tables(int64_t in_size, int64_t out_size, int filter, int align_cor
   if (!g.ok) return cuda_fail(g.err, "cudaSetDevice");
   std::shared_ptr<AxisTables> t;
   const int td = dtype == AA_F64 ? AA_F64 : AA_F32;
-  if ((rc = get_axis_tables(device, in_size, out_size, filter, align_corners, td, stream, &t)) != AA_OK) return rc;
+  if ((rc = get_axis_tables(device, in_size, out_size, filter, align_corners, td, scale_factor, stream, &t)) != AA_OK) return rc;
   const int NT = 256;
   widen_i32_i64<<<(unsigned)((out_size + NT - 1) / NT), NT, 0, stream>>>(t->xmin, dst->xmin, out_size);
   AA_LAUNCH_CHECK("widen xmin");
@@ -230,17 +269,39 @@ int aa_warm_tables(int64_t in_h, int64_t in_w, int64_t out_h, int64_t out_w, int
   if ((rc = check_filter(filter)) != AA_OK) return rc;
   DeviceGuard g(device);
   if (!g.ok) return cuda_fail(g.err, "cudaSetDevice");
-  std::shared_ptr<AxisTables> t;
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  std::shared_ptr<AxisTables> th, tw;
   const int td = dtype == AA_F64 ? AA_F64 : AA_F32;
-  if ((rc = get_axis_tables(device, in_h, out_h, filter, align_corners, td, (cudaStream_t)cuda_stream, &t)) != AA_OK) return rc;
-  if (td == AA_F32 && t->kt_max <= 6) {
-    rc = ensure_slot_tables(t.get(), t->kt_max <= 3 ? 3 : t->kt_max, (cudaStream_t)cuda_stream);
-    if (rc != AA_OK && rc != AA_ERR_UNSUPPORTED) return rc;
+  if ((rc = get_axis_tables(device, in_h, out_h, filter, align_corners, td, 0.0, stream, &th)) != AA_OK) return rc;
+  if ((rc = get_axis_tables(device, in_w, out_w, filter, align_corners, td, 0.0, stream, &tw)) != AA_OK) return rc;
+  if (td == AA_F32) {
+    // the derived tables of every path a later forward / backward call of this shape may take
+    if (th->kt_max <= 6) {
+      rc = ensure_slot_tables(th.get(), th->kt_max <= 3 ? 3 : th->kt_max, stream);
+      if (rc != AA_OK && rc != AA_ERR_UNSUPPORTED) return rc;
+    }
+    if (th->xsize_max <= 6) {
+      rc = ensure_slot_tables_adj(th.get(), th->xsize_max <= 3 ? 3 : th->xsize_max, stream);
+      if (rc != AA_OK && rc != AA_ERR_UNSUPPORTED) return rc;
+    }
+    if (dtype == AA_U8 && vmma_auto(th.get(), tw.get())) {
+      rc = vmma_warm(th.get(), stream);
+      if (rc != AA_OK && rc != AA_ERR_UNSUPPORTED) return rc;
+    }
   }
-  return get_axis_tables(device, in_w, out_w, filter, align_corners, td, (cudaStream_t)cuda_stream, &t);
+  // after this the tables are complete for every stream (and for CUDA-graph capture)
+  AA_CUDA_TRY(cudaStreamSynchronize(stream));
+  return AA_OK;
 }
 
 int aa_clear_table_cache(void) { return clear_table_cache(); }
+
+int aa_check_device(int device) {
+  if (device < 0 || device >= 64) return fail(AA_ERR_INVALID, "bad device ordinal");
+  DeviceGuard g(device);
+  if (!g.ok) return cuda_fail(g.err, "cudaSetDevice");
+  return vmma_check_watchdog(device);
+}
 
 int aa_resize_forward(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align_corners, uint32_t flags,
                       void* cuda_stream) {
@@ -253,8 +314,13 @@ int aa_resize_forward_ex(const aa_tensor_desc* in, const aa_tensor_desc* out, in
   return forward_impl(in, out, filter, align_corners, flags, (cudaStream_t)cuda_stream, epilogue);
 }
 
-int aa_resize_backward(const aa_tensor_desc* gout, const aa_tensor_desc* gin, int filter, int align_corners, uint32_t flags,
-                       void* cuda_stream) {
+int aa_resize_forward_sf(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align_corners,
+                         const aa_scales* scales, uint32_t flags, void* cuda_stream) {
+  return forward_impl(in, out, filter, align_corners, flags, (cudaStream_t)cuda_stream, nullptr, scales);
+}
+
+static int backward_impl(const aa_tensor_desc* gout, const aa_tensor_desc* gin, int filter, int align_corners, uint32_t flags,
+                         void* cuda_stream, const aa_scales* sc) {
   int rc;
   Layout lo, li;
   if ((rc = check_filter(filter)) != AA_OK) return rc;
@@ -264,8 +330,8 @@ int aa_resize_backward(const aa_tensor_desc* gout, const aa_tensor_desc* gin, in
   DeviceGuard g(gout->device);
   if (!g.ok) return cuda_fail(g.err, "cudaSetDevice");
   std::shared_ptr<AxisTables> th, tw;
-  if ((rc = get_axis_tables(gout->device, gin->h, gout->h, filter, align_corners, gout->dtype, stream, &th)) != AA_OK) return rc;
-  if ((rc = get_axis_tables(gout->device, gin->w, gout->w, filter, align_corners, gout->dtype, stream, &tw)) != AA_OK) return rc;
+  if ((rc = get_axis_tables(gout->device, gin->h, gout->h, filter, align_corners, gout->dtype, sc ? sc->scale_h : 0.0, stream, &th)) != AA_OK) return rc;
+  if ((rc = get_axis_tables(gout->device, gin->w, gout->w, filter, align_corners, gout->dtype, sc ? sc->scale_w : 0.0, stream, &tw)) != AA_OK) return rc;
   if (gout->dtype == AA_F32 && !(flags & AA_FLAG_FORCE_GENERAL)) {
     // few adjoint taps (the forward was a downsampling): write-bound tile kernel; many taps (the forward was
     // an upsampling): the backward is the input-bound direction -> streaming kernel with the roles swapped
@@ -279,6 +345,15 @@ int aa_resize_backward(const aa_tensor_desc* gout, const aa_tensor_desc* gin, in
   }
   return launch_general(gout->data, gout->dtype, lo, gin->data, gin->dtype, li, adj_axis(th.get()), adj_axis(tw.get()),
                         /*exact=*/false, OutEpi(), stream);
+}
+
+int aa_resize_backward(const aa_tensor_desc* gout, const aa_tensor_desc* gin, int filter, int align_corners, uint32_t flags,
+                       void* cuda_stream) {
+  return backward_impl(gout, gin, filter, align_corners, flags, cuda_stream, nullptr);
+}
+int aa_resize_backward_sf(const aa_tensor_desc* gout, const aa_tensor_desc* gin, int filter, int align_corners,
+                          const aa_scales* scales, uint32_t flags, void* cuda_stream) {
+  return backward_impl(gout, gin, filter, align_corners, flags, cuda_stream, scales);
 }
 
 int aa_resize_backward_nonaa_bilinear(const aa_tensor_desc* gout, const aa_tensor_desc* gin, int align_corners,
@@ -307,21 +382,48 @@ std::mutex g_host_mu;
 HostCtx g_host_ctx[64];
 }  // namespace
 
+// dense NCHW (fmt 0) or NHWC (fmt 1) check for host buffers: the staging copies are flat memcpys
+static int dense_format(const aa_tensor_desc* t, int* fmt) {
+  auto ok = [](int64_t size, int64_t stride, int64_t want) { return size == 1 || stride == want; };
+  const bool cf = ok(t->w, t->stride_w, 1) && ok(t->h, t->stride_h, t->w) && ok(t->c, t->stride_c, t->h * t->w) &&
+                  ok(t->n, t->stride_n, t->c * t->h * t->w);
+  const bool cl = ok(t->c, t->stride_c, 1) && ok(t->w, t->stride_w, t->c) && ok(t->h, t->stride_h, t->w * t->c) &&
+                  ok(t->n, t->stride_n, t->c * t->h * t->w);
+  if (!cf && !cl) return AA_ERR_UNSUPPORTED;
+  *fmt = (cf && cl) ? -1 : (cl ? 1 : 0);  // -1: both readings describe the same bytes
+  return AA_OK;
+}
+static void dense_strides(aa_tensor_desc* t, int fmt) {
+  if (fmt == 1) { t->stride_c = 1; t->stride_w = t->c; t->stride_h = t->w * t->c; t->stride_n = t->h * t->w * t->c; }
+  else { t->stride_w = 1; t->stride_h = t->w; t->stride_c = t->h * t->w; t->stride_n = t->c * t->h * t->w; }
+}
+
 int aa_resize_forward_host(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align_corners,
                            uint32_t flags) {
   int rc;
+  // everything is validated BEFORE the first byte of the host buffers is touched
   if ((rc = check_desc(in, "input")) != AA_OK) return rc;
   if ((rc = check_desc(out, "output")) != AA_OK) return rc;
+  if ((rc = check_filter(filter)) != AA_OK) return rc;
   if (in->n != out->n || in->c != out->c) return fail(AA_ERR_INVALID, "input and output must agree in n and c");
+  if (in->dtype > AA_F64) return fail(AA_ERR_INVALID, "input dtype must be u8, f32 or f64");
+  if (out->dtype > AA_F64) return fail(AA_ERR_UNSUPPORTED, "host path: u8/f32/f64 outputs only");
+  {
+    const int tdtype = in->dtype == AA_F64 ? AA_F64 : AA_F32;
+    if (out->dtype != tdtype && !(out->dtype == AA_U8 && tdtype == AA_F32))
+      return fail(AA_ERR_INVALID, "output dtype must be f32 (or u8) for u8/f32 inputs and f64 for f64 inputs");
+  }
   if (in->n == 0) return AA_OK;
   const int dev = in->device;
   if (dev < 0 || dev >= 64) return fail(AA_ERR_INVALID, "bad device ordinal");
+  int ifmt = 0, ofmt = 0;
+  if (dense_format(in, &ifmt) != AA_OK || dense_format(out, &ofmt) != AA_OK)
+    return fail(AA_ERR_UNSUPPORTED, "host path needs fully dense NCHW or NHWC buffers (no padded rows, slices or views)");
+  if (ifmt >= 0 && ofmt >= 0 && ifmt != ofmt) return fail(AA_ERR_UNSUPPORTED, "input and output must use the same memory format");
+  const int fmt = ifmt >= 0 ? ifmt : (ofmt >= 0 ? ofmt : 0);
   const size_t ies = in->dtype == AA_U8 ? 1 : (in->dtype == AA_F32 ? 4 : 8);
-  if (out->dtype > AA_F64) return fail(AA_ERR_UNSUPPORTED, "host path: u8/f32/f64 outputs only");
   const size_t oes = out->dtype == AA_U8 ? 1 : (out->dtype == AA_F32 ? 4 : 8);
   const size_t img_in = (size_t)in->c * in->h * in->w, img_out = (size_t)out->c * out->h * out->w;
-  if ((in->n > 1 && (size_t)in->stride_n != img_in) || (out->n > 1 && (size_t)out->stride_n != img_out))
-    return fail(AA_ERR_UNSUPPORTED, "host path needs densely packed images (stride_n == c*h*w)");
   DeviceGuard g(dev);
   if (!g.ok) return cuda_fail(g.err, "cudaSetDevice");
   std::lock_guard<std::mutex> lock(g_host_mu);
@@ -351,22 +453,38 @@ int aa_resize_forward_host(const aa_tensor_desc* in, const aa_tensor_desc* out, 
     C.cap_in = need_in;
     C.cap_out = need_out;
   }
+  // the staging buffers are dense by construction: their descs are rebuilt, never copied from the caller's strides
+  aa_tensor_desc di = *in, dd_out = *out;
+  dense_strides(&di, fmt);
+  dense_strides(&dd_out, fmt);
   int64_t done = 0;
-  for (int i = 0; done < in->n; i++) {
+  rc = AA_OK;
+  std::string err;
+  for (int i = 0; done < in->n && rc == AA_OK; i++) {
     const int s = i % HostCtx::NS;
     const int64_t nb = std::min<int64_t>(per, in->n - done);
-    aa_tensor_desc di = *in, dd_out = *out;
     di.data = C.din[s]; di.n = nb;
     dd_out.data = C.dout[s]; dd_out.n = nb;
-    AA_CUDA_TRY(cudaMemcpyAsync(C.din[s], (const char*)in->data + (size_t)done * img_in * ies, (size_t)nb * img_in * ies,
-                                cudaMemcpyHostToDevice, C.streams[s]));
-    if ((rc = forward_impl(&di, &dd_out, filter, align_corners, flags, C.streams[s])) != AA_OK) return rc;
-    AA_CUDA_TRY(cudaMemcpyAsync((char*)out->data + (size_t)done * img_out * oes, C.dout[s], (size_t)nb * img_out * oes,
-                                cudaMemcpyDeviceToHost, C.streams[s]));
+    cudaError_t e = cudaMemcpyAsync(C.din[s], (const char*)in->data + (size_t)done * img_in * ies, (size_t)nb * img_in * ies,
+                                    cudaMemcpyHostToDevice, C.streams[s]);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(H2D)"); break; }
+    if ((rc = forward_impl(&di, &dd_out, filter, align_corners, flags, C.streams[s])) != AA_OK) break;
+    e = cudaMemcpyAsync((char*)out->data + (size_t)done * img_out * oes, C.dout[s], (size_t)nb * img_out * oes,
+                        cudaMemcpyDeviceToHost, C.streams[s]);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(D2H)"); break; }
     done += nb;
   }
-  for (int i = 0; i < HostCtx::NS; i++) AA_CUDA_TRY(cudaStreamSynchronize(C.streams[i]));
-  return AA_OK;
+  if (rc != AA_OK) err = g_err;
+  // success or failure: nothing of this call may still be writing `out` (or reading `in`) when it returns
+  for (int i = 0; i < HostCtx::NS; i++) {
+    const cudaError_t e = cudaStreamSynchronize(C.streams[i]);
+    if (e != cudaSuccess && rc == AA_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
+  }
+  if (rc != AA_OK) {
+    if (!err.empty()) g_err = err;
+    return rc;
+  }
+  return vmma_check_watchdog(dev);
 }
 
 }  // extern "C"

@@ -295,14 +295,14 @@ __global__ void __launch_bounds__(NT) aa_band_kernel(const BParams P) {
 }
 
 template <int KH, int KW, bool GEN, typename in_t>
-int launch_k(BParams& P, int64_t planes, const BandedAxis& ah, int nc_max, cudaStream_t stream) {
+int launch_k(BParams& P, int64_t planes, const BandedAxis& ah, int nc_max, cudaStream_t stream, GeomPlan& G) {
   constexpr int HR = (KH + 1 + 3) / 4;
   P.pcp = (nc_max + (KW - 1) * P.Ci + 3 + 3) & ~3;  // + up to 3 lead columns (aligned 16-byte copies); multiple of 4
   // chunk height: 16 output rows measured best at 0.75x..1x (bilinear and bicubic), 8 when 16 do not fit 4 CTAs/SM
   const int tys[2] = {16, 8};
   const size_t limits[2] = {56 * 1024, 113 * 1024};
-  int best_ty = 0, best_pr = 0;
-  size_t best_smem = 0;
+  int best_ty = G.ty, best_pr = G.nr;
+  size_t best_smem = G.smem;
   for (int li = 0; li < 2 && !best_ty; li++)
     for (int ti = 0; ti < 2 && !best_ty; ti++) {
       const int TY = tys[ti];
@@ -317,6 +317,7 @@ int launch_k(BParams& P, int64_t planes, const BandedAxis& ah, int nc_max, cudaS
       best_ty = TY; best_pr = (int)nr; best_smem = smem;
     }
   if (!best_ty) return fail(AA_ERR_UNSUPPORTED, "band: input patch too large; use the streaming/general path");
+  G.ty = best_ty; G.nr = best_pr; G.smem = best_smem;
   P.ty = best_ty; P.pr = best_pr; P.tr = best_pr + KH - 1;
   P.n_chunks = (P.out_h + P.ty - 1) / P.ty;
   if (planes <= 0 || P.n_chunks <= 0) return AA_OK;
@@ -328,7 +329,7 @@ int launch_k(BParams& P, int64_t planes, const BandedAxis& ah, int nc_max, cudaS
   nseg = (P.n_chunks + P.seg_chunks - 1) / P.seg_chunks;
   if (nseg > 65535) return fail(AA_ERR_UNSUPPORTED, "band: too many row segments");
   auto kern = aa_band_kernel<KH, KW, GEN, in_t>;
-  if (best_smem > 48 * 1024) AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best_smem));
+  AA_CUDA_TRY(ensure_smem_attr(kern, ah.device, best_smem));
   for (int64_t p0 = 0; p0 < planes; p0 += 65535) {
     P.plane0 = p0;
     const dim3 grid((unsigned)P.tiles_x, (unsigned)nseg, (unsigned)std::min<int64_t>(65535, planes - p0));
@@ -339,26 +340,26 @@ int launch_k(BParams& P, int64_t planes, const BandedAxis& ah, int nc_max, cudaS
 }
 
 template <int KH, int KW, typename in_t>
-int launch_gen(BParams& P, int64_t planes, const BandedAxis& ah, int nc_max, cudaStream_t stream) {
-  if (P.epi.generic()) return launch_k<KH, KW, true, in_t>(P, planes, ah, nc_max, stream);  // decode-adjacent epilogue
-  return launch_k<KH, KW, false, in_t>(P, planes, ah, nc_max, stream);
+int launch_gen(BParams& P, int64_t planes, const BandedAxis& ah, int nc_max, cudaStream_t stream, GeomPlan& G) {
+  if (P.epi.generic()) return launch_k<KH, KW, true, in_t>(P, planes, ah, nc_max, stream, G);  // decode-adjacent epilogue
+  return launch_k<KH, KW, false, in_t>(P, planes, ah, nc_max, stream, G);
 }
 
 template <int KH, typename in_t>
-int launch_kh(BParams& P, int kw, int64_t nb, const BandedAxis& ah, int nc, cudaStream_t s) {
-  if (kw <= 2) return launch_gen<KH, 2, in_t>(P, nb, ah, nc, s);
-  if (kw <= 3) return launch_gen<KH, 3, in_t>(P, nb, ah, nc, s);
-  if (kw <= 5) return launch_gen<KH, 5, in_t>(P, nb, ah, nc, s);
-  if (kw <= 7) return launch_gen<KH, 7, in_t>(P, nb, ah, nc, s);
+int launch_kh(BParams& P, int kw, int64_t nb, const BandedAxis& ah, int nc, cudaStream_t s, GeomPlan& G) {
+  if (kw <= 2) return launch_gen<KH, 2, in_t>(P, nb, ah, nc, s, G);
+  if (kw <= 3) return launch_gen<KH, 3, in_t>(P, nb, ah, nc, s, G);
+  if (kw <= 5) return launch_gen<KH, 5, in_t>(P, nb, ah, nc, s, G);
+  if (kw <= 7) return launch_gen<KH, 7, in_t>(P, nb, ah, nc, s, G);
   return fail(AA_ERR_UNSUPPORTED, "band: more than 7 horizontal taps");
 }
 
 template <typename in_t>
-int launch_in(BParams& P, int kh, int kw, int64_t nb, const BandedAxis& ah, int nc, cudaStream_t s) {
-  if (kh <= 2) return launch_kh<2, in_t>(P, kw, nb, ah, nc, s);
-  if (kh <= 3) return launch_kh<3, in_t>(P, kw, nb, ah, nc, s);
-  if (kh <= 5) return launch_kh<5, in_t>(P, kw, nb, ah, nc, s);
-  if (kh <= 7) return launch_kh<7, in_t>(P, kw, nb, ah, nc, s);
+int launch_in(BParams& P, int kh, int kw, int64_t nb, const BandedAxis& ah, int nc, cudaStream_t s, GeomPlan& G) {
+  if (kh <= 2) return launch_kh<2, in_t>(P, kw, nb, ah, nc, s, G);
+  if (kh <= 3) return launch_kh<3, in_t>(P, kw, nb, ah, nc, s, G);
+  if (kh <= 5) return launch_kh<5, in_t>(P, kw, nb, ah, nc, s, G);
+  if (kh <= 7) return launch_kh<7, in_t>(P, kw, nb, ah, nc, s, G);
   return fail(AA_ERR_UNSUPPORTED, "band: more than 7 vertical taps");
 }
 
@@ -376,22 +377,38 @@ int launch_band(const void* in, int in_dtype, const Layout& lin, void* out, cons
   P.w_start = aw.start; P.w_size = aw.size; P.w_w = (const float*)aw.w; P.w_pitch = aw.pitch;
   P.in_h = (int)ah.n_in; P.in_wf = (int)(aw.n_in * Ci); P.out_h = (int)ah.n_out; P.out_wf = (int)(aw.n_out * Ci);
   P.tiles_x = (P.out_wf + TXF - 1) / TXF;
-  // exact column plan from the host mirror of the table (the row plan depends on the chunk height)
-  int64_t nc = 1;
-  for (int64_t f0 = 0; f0 < P.out_wf; f0 += TXF) {
-    const int64_t f1 = std::min<int64_t>(P.out_wf, f0 + TXF) - 1;
-    const int64_t x0 = f0 / Ci, x1 = f1 / Ci;
-    nc = std::max<int64_t>(nc, ((int64_t)aw.h_start[x1] + aw.h_size[x1] - aw.h_start[x0]) * Ci);
+  const GeomKey gkey{ah.id, aw.id, 2 | (Ci << 8) | (in_dtype << 24) | ((epi.generic() ? 1 : 0) << 28)};
+  GeomPlan G;
+  const bool planned = geom_lookup(gkey, &G);
+  if (planned && !G.ty) return fail(AA_ERR_UNSUPPORTED, "band: input patch too large; use the streaming/general path");
+  int64_t nc = G.nc;
+  if (!planned) {
+    // exact column plan from the host mirror of the table (the row plan depends on the chunk height)
+    nc = 1;
+    for (int64_t f0 = 0; f0 < P.out_wf; f0 += TXF) {
+      const int64_t f1 = std::min<int64_t>(P.out_wf, f0 + TXF) - 1;
+      const int64_t x0 = f0 / Ci, x1 = f1 / Ci;
+      nc = std::max<int64_t>(nc, ((int64_t)aw.h_start[x1] + aw.h_size[x1] - aw.h_start[x0]) * Ci);
+    }
+    G.nc = (int)std::min<int64_t>(nc, 1 << 30);
+    if (nc > 4096) {
+      geom_store(gkey, G);
+      return fail(AA_ERR_UNSUPPORTED, "band: input patch too large; use the streaming/general path");
+    }
   }
-  if (nc > 4096) return fail(AA_ERR_UNSUPPORTED, "band: input patch too large; use the streaming/general path");
   P.vec_load = in_dtype == AA_F32 && ((uintptr_t)in) % 16 == 0 && lin.stride_h % 4 == 0 && lin.stride_n % 4 == 0 &&
                (lin.Cp == 1 || lin.stride_p % 4 == 0) && P.in_wf % 4 == 0;
   P.dci = FastDiv::make((uint32_t)Ci);
   P.dcp = FastDiv::make((uint32_t)(lin.Cp > 0 ? lin.Cp : 1));
   P.vec_store = (((uintptr_t)out) % (epi.kind == 1 ? 4 : 16) == 0) && (lout.stride_h % 4 == 0) && (lout.stride_n % 4 == 0) &&
                 (lout.Cp == 1 || lout.stride_p % 4 == 0);
-  if (in_dtype == AA_F32) return launch_in<float>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream);
-  return launch_in<uint8_t>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream);
+  const int rc = in_dtype == AA_F32 ? launch_in<float>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream, G)
+                                    : launch_in<uint8_t>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream, G);
+  if (!planned && (rc == AA_OK || rc == AA_ERR_UNSUPPORTED) && lin.planes > 0) {
+    if (rc == AA_ERR_UNSUPPORTED) G.ty = 0;
+    geom_store(gkey, G);
+  }
+  return rc;
 }
 
 }  // namespace aa

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -45,14 +46,21 @@ struct AxisTables {
   int64_t in = 0, out = 0;
   int filter = 0, align = 0;
   int dtype = AA_F32;  // AA_F32 or AA_F64: scalar_t of the table arithmetic
+  double user_scale = 0.0;  // caller-provided scale factor (0 = none: scale = in/out)
+  // cache bookkeeping
+  uint64_t id = 0;        // unique per built table: launch-plan caches key on it (never on the address)
+  uint64_t last_use = 0;  // LRU clock
+  cudaEvent_t ready = nullptr;        // recorded after the table kernels; null once known complete
+  cudaStream_t build_stream = nullptr;
+  std::mutex mu;          // guards the lazily built derived tables below (slot, slot_adj, vq)
   // host-side scalars (computed with the same IEEE operations as the device kernel)
   float scale_f = 0.f, support_f = 0.f;
   double scale_d = 0.0, support_d = 0.0;
   int K = 0;         // padded taps per output (:210)
   int KT = 0;        // adjoint row pitch (>= kt_max)
-  int kt_max = 0;    // max number of outputs covering one input index (measured on device)
-  int xsize_max = 0; // max window length (measured on device)
-  int monotone = 1;  // device-verified: xmin and xmin+xsize non-decreasing
+  int kt_max = 0;    // max number of outputs covering one input index
+  int xsize_max = 0; // max window length
+  int monotone = 1;  // verified: xmin and xmin+xsize non-decreasing
   // device buffers (one allocation, `block`)
   void* block = nullptr;
   int32_t* xmin = nullptr;   // [out]
@@ -70,20 +78,33 @@ struct AxisTables {
   // forward-output row o, the forward weights w[o][0..A) belong to the open grad_in rows xmin[o]+k
   int slot_adj_A = 0, slot_adj_RS = 0;
   float* slot_adj = nullptr;  // [out][RS]
+  // tensor-core vertical pass (aa_vmma.cu): the forward weights of each block of `oyb` output rows as a
+  // [ksteps*32 input rows][128] int8 matrix (3 balanced base-256 digits per weight, 128-byte-swizzled rows)
+  int8_t* vq = nullptr;       // [vq_noyb][vq_ksteps*32][128]
+  float* vq_meta = nullptr;   // {c0, c1, c2, K0, (int) s}
+  int vq_ksteps = 0, vq_noyb = 0;
   // host mirrors of the integer tables (for launch planning)
   std::vector<int32_t> h_xmin, h_xsize, h_omin, h_osize;
   ~AxisTables();
 };
 
-// Returns the cached tables, building them on `stream` on a miss (one sync on a miss only).
-int get_axis_tables(int device, int64_t in, int64_t out, int filter, int align, int dtype,
+// Returns the cached tables, building them on `stream` on a miss (stream-ordered, no synchronisation; users on
+// other streams are made to wait on the build's event).  The cache is an LRU of AA_TABLE_CACHE_MAX (256) entries.
+int get_axis_tables(int device, int64_t in, int64_t out, int filter, int align, int dtype, double user_scale,
                     cudaStream_t stream, std::shared_ptr<AxisTables>* result);
+void table_cache_stats(int64_t* entries, int64_t* hits, int64_t* misses, int64_t* evictions);
+void host_int_tables(int64_t in, int64_t out, int filter, int align, int dtype, double user_scale, int32_t* xmin_o,
+                     int32_t* xsize_o);
+void tile_plan_clear();
 // Makes sure t->slot exists for `A` accumulators (A in 3..6); launches one tiny kernel on first use.
 int ensure_slot_tables(AxisTables* t, int A, cudaStream_t stream);
 int ensure_slot_tables_adj(AxisTables* t, int A, cudaStream_t stream);
+// Quantised weight matrices of the tensor-core vertical pass; AA_ERR_UNSUPPORTED when a block of `oyb` output rows
+// spans more than max_ksteps*kstep input rows.
+int ensure_vq_tables(AxisTables* t, int oyb, int kstep, int max_ksteps, cudaStream_t stream);
 int clear_table_cache();
 // Host-only K computation (no device), same arithmetic as the table kernel.
-int host_interp_size(int64_t in, int64_t out, int filter, int align, int dtype);
+int host_interp_size(int64_t in, int64_t out, int filter, int align, int dtype, double user_scale = 0.0);
 
 // ---- layout --------------------------------------------------------------------------------
 // Both supported memory formats are expressed as `planes` independent 2-D images whose rows are
@@ -220,7 +241,37 @@ struct BandedAxis {  // one axis of a banded separable apply: out index i reads 
   int64_t n_in, n_out;
   const int32_t* h_start;  // host mirrors of start/size (launch planning)
   const int32_t* h_size;
+  uint64_t id;             // identity of the tables for the launch-plan caches (AxisTables::id * 2 + direction)
+  int device;
 };
+
+// Launch-geometry cache of the few-tap kernels (aa_tile.cu, aa_band.cu): what the host derives by scanning the table
+// mirrors (patch sizes, tile height, shared memory) is kept per (tables, interleave, kernel family), so a steady-state
+// call is a map lookup + one launch, like the streaming kernel's plan cache.
+struct GeomKey {
+  uint64_t ah, aw;
+  int tag;  // family | Ci << 8 | input dtype << 24 | generic epilogue << 28
+  bool operator<(const GeomKey& o) const {
+    if (ah != o.ah) return ah < o.ah;
+    if (aw != o.aw) return aw < o.aw;
+    return tag < o.tag;
+  }
+};
+struct GeomPlan {
+  int nc = 0;       // widest input patch (flat elements)
+  int vr4 = 0;      // tile: 4-rows-per-step variant
+  int ty = 0;       // chosen tile / chunk height (0: not eligible)
+  int nr = 0;       // patch rows for that height
+  size_t smem = 0;
+};
+bool geom_lookup(const GeomKey& k, GeomPlan* p);
+void geom_store(const GeomKey& k, const GeomPlan& p);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of per call
+cudaError_t ensure_smem_attr_impl(const void* kern, int device, size_t smem);
+template <typename K>
+inline cudaError_t ensure_smem_attr(K kern, int device, size_t smem) {
+  return ensure_smem_attr_impl(reinterpret_cast<const void*>(kern), device, smem);
+}
 
 // General gather-form tile kernel: out = Ah * in * Aw^T per plane, horizontal pass first.
 // exact=true: separate multiply and add (bit-identical to the reference's C++), else FMA.
@@ -247,6 +298,14 @@ int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, co
 // i.e. the backward is the many-taps, input-bound direction.  AA_ERR_UNSUPPORTED when not eligible.
 int launch_stream_adjoint(const void* gout, const Layout& lo, void* gin, const Layout& li, AxisTables* th, AxisTables* tw,
                           cudaStream_t stream);
+
+// uint8 input, downsampling in H: vertical pass on the tensor cores (tcgen05 kind::i8 + TMA), horizontal pass as a gather
+// (aa_vmma.cu).  AA_ERR_UNSUPPORTED when not eligible.
+int launch_vmma(const void* in, const Layout& lin, void* out, const Layout& lout, AxisTables* th, AxisTables* tw, int64_t H,
+                int64_t W, int64_t oH, int64_t oW, OutEpi epi, cudaStream_t stream);
+int vmma_check_watchdog(int device);
+int vmma_warm(AxisTables* th, cudaStream_t stream);  // everything a later launch_vmma would allocate or synchronise for
+void vmma_plan_clear();
 
 int launch_backward_nonaa(const void* gout, void* gin, int dtype, const Layout& lout, const Layout& lin,
                           int64_t oH, int64_t oW, int64_t H, int64_t W, int align, cudaStream_t stream);

@@ -189,6 +189,10 @@ __device__ __forceinline__ Lam<T> src_index_rn(T ratio, int64_t o, int64_t in, i
     real = sub_rn(mul_rn(ratio, add_rn((T)o, (T)0.5)), (T)0.5);
     if (real < (T)0) real = (T)0;
   }
+  // guard_index_and_lambda of the INSTALLED torch (2.11, ATen/native/UpSample.h) -- the header oracle/_ref compiles
+  // against -- is min(static_cast<int64_t>(floorf(real)), in - 1): floorf, i.e. through float even when T is double
+  // (the 2021 header had static_cast<int64_t>(real); for real >= 0 the two differ only where float rounding crosses an
+  // integer).  Kept bit-identical to what the oracle computes here (tests/test_backward_gpu.py, f64 non-AA backward).
   int64_t idx = (int64_t)floorf((float)real);
   if (idx > in - 1) idx = in - 1;
   T lam = sub_rn(real, (T)idx);

@@ -317,6 +317,7 @@ bool plan_lookup(const PlanKey& k, Plan* p) {
 }
 void plan_store(const PlanKey& k, const Plan& p) {
   std::lock_guard<std::mutex> lock(g_plan_mu);
+  if (g_plans.size() > 4096) g_plans.clear();  // plans of evicted tables: bounded, rebuilt on demand
   g_plans[k] = p;
 }
 void plan_clear() {
@@ -370,7 +371,7 @@ int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, co
   P.slot_h = th->slot; P.RS = th->slot_RS;
   P.xmin_h = th->xmin; P.xsize_h = th->xsize;
   P.xmin_w = tw->xmin; P.xsize_w = tw->xsize; P.w_w = (const float*)tw->w; P.Kw = tw->K;
-  const StreamTables T{th, tw, 0, th->h_xmin.data(), th->h_xsize.data(), oH, tw->h_xmin.data(), tw->h_xsize.data(), W, oW};
+  const StreamTables T{th->id, tw->id, 0, th->h_xmin.data(), th->h_xsize.data(), oH, tw->h_xmin.data(), tw->h_xsize.data(), W, oW};
   return dispatch_A(P, A, in_dtype, vec, T, th->device, flags, stream);
 }
 
@@ -396,7 +397,7 @@ int launch_stream_adjoint(const void* gout, const Layout& lo, void* gin, const L
   P.slot_h = th->slot_adj; P.RS = th->slot_adj_RS;
   P.xmin_h = th->omin; P.xsize_h = th->osize;
   P.xmin_w = tw->omin; P.xsize_w = tw->osize; P.w_w = (const float*)tw->wT; P.Kw = tw->KT;
-  const StreamTables T{th, tw, 1, th->h_omin.data(), th->h_osize.data(), H, tw->h_omin.data(), tw->h_osize.data(), oW, W};
+  const StreamTables T{th->id, tw->id, 1, th->h_omin.data(), th->h_osize.data(), H, tw->h_omin.data(), tw->h_osize.data(), oW, W};
   return dispatch_A(P, A, AA_F32, vec, T, th->device, 0u, stream);
 }
 

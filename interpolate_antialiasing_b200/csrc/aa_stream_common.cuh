@@ -328,7 +328,7 @@ inline size_t strip_table_bytes(const SParams& P) {
 // Host-side view of the tables for one direction of the banded separable apply (forward, or adjoint when
 // the backward is the downsampling-shaped direction).  "Output rows" are the rows the kernel produces.
 struct StreamTables {
-  const void *key_h, *key_w;              // identity for the plan cache
+  uint64_t key_h, key_w;                  // identity for the plan cache (AxisTables::id)
   int dir;                                // 0 forward, 1 adjoint
   const int32_t *hh_start, *hh_size;      // host: per output row, first input row and window length
   int64_t n_out_h;
@@ -416,7 +416,7 @@ inline int plan_stream(SParams& P, const StreamTables& T, int cap, int aln, int 
 // Launch plans are cached per (tables, interleave, kernel variant): the steady-state host cost of a
 // call is one map lookup + one kernel launch (no occupancy queries, no attribute calls).
 struct PlanKey {
-  const void *th, *tw;
+  uint64_t th, tw;
   int Ci, kid;
   bool operator<(const PlanKey& o) const {
     if (th != o.th) return th < o.th;

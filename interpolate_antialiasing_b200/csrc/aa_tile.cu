@@ -18,6 +18,9 @@
 // bit-exact non-FMA order is aa_general.cu's job).
 #include <algorithm>
 
+#include <map>
+#include <mutex>
+
 #include "aa_common.cuh"
 
 namespace aa {
@@ -296,13 +299,18 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
 }
 
 template <int KH, int KW, int VR, bool GEN, typename in_t>
-int launch_ty(TParams& P, int TY, int64_t planes, const BandedAxis& ah, size_t smem_limit, cudaStream_t stream) {
+int launch_ty(TParams& P, int TY, int64_t planes, const BandedAxis& ah, size_t smem_limit, cudaStream_t stream, GeomPlan& G) {
   using R = VRec<KH, VR>;
-  // exact row plan for this tile height from the host mirror
   int64_t nr = 1;
-  for (int64_t y0 = 0; y0 < P.out_h; y0 += TY) {
-    const int64_t y1 = std::min<int64_t>(P.out_h, y0 + TY) - 1;
-    nr = std::max<int64_t>(nr, (int64_t)ah.h_start[y1] + ah.h_size[y1] - ah.h_start[y0]);
+  if (G.ty) {  // planned before: only the chosen tile height is tried, with its recorded patch height
+    if (G.ty != TY) return AA_ERR_UNSUPPORTED;
+    nr = G.nr;
+  } else {
+    // exact row plan for this tile height from the host mirror
+    for (int64_t y0 = 0; y0 < P.out_h; y0 += TY) {
+      const int64_t y1 = std::min<int64_t>(P.out_h, y0 + TY) - 1;
+      nr = std::max<int64_t>(nr, (int64_t)ah.h_start[y1] + ah.h_size[y1] - ah.h_start[y0]);
+    }
   }
   if (nr > 1024) return fail(AA_ERR_UNSUPPORTED, "tile: input patch too large; use the streaming/general path");
   P.ty = TY;
@@ -314,7 +322,8 @@ int launch_ty(TParams& P, int TY, int64_t planes, const BandedAxis& ah, size_t s
   if (planes <= 0) return AA_OK;
   if (P.tiles_y > 65535) return fail(AA_ERR_UNSUPPORTED, "tile: too many row tiles");
   auto kern = aa_tile_kernel<KH, KW, VR, GEN, in_t>;
-  if (smem > 48 * 1024) AA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  AA_CUDA_TRY(ensure_smem_attr(kern, ah.device, smem));
+  G.ty = TY; G.nr = (int)nr; G.smem = smem;
   for (int64_t p0 = 0; p0 < planes; p0 += 65535) {
     P.plane0 = p0;
     const dim3 grid((unsigned)P.tiles_x, (unsigned)P.tiles_y, (unsigned)std::min<int64_t>(65535, planes - p0));
@@ -325,53 +334,88 @@ int launch_ty(TParams& P, int TY, int64_t planes, const BandedAxis& ah, size_t s
 }
 
 template <int KH, int KW, int VR, typename in_t>
-int launch_vr(TParams& P, int64_t planes, const BandedAxis& ah, cudaStream_t stream) {
+int launch_vr(TParams& P, int64_t planes, const BandedAxis& ah, cudaStream_t stream, GeomPlan& G) {
   // tall tiles amortise the per-CTA setup when the patch stays small (upsampling-like gathers)
   if (P.epi.generic()) {  // decode-adjacent epilogue: its own instantiations, two tile heights
-    int rg = launch_ty<KH, KW, VR, true, in_t>(P, 32, planes, ah, 72 * 1024, stream);
+    int rg = launch_ty<KH, KW, VR, true, in_t>(P, 32, planes, ah, 72 * 1024, stream, G);
     if (rg != AA_ERR_UNSUPPORTED) return rg;
-    return launch_ty<KH, KW, VR, true, in_t>(P, 16, planes, ah, 72 * 1024, stream);
+    return launch_ty<KH, KW, VR, true, in_t>(P, 16, planes, ah, 72 * 1024, stream, G);
   }
-  int rc = launch_ty<KH, KW, VR, false, in_t>(P, 64, planes, ah, 40 * 1024, stream);
+  int rc = launch_ty<KH, KW, VR, false, in_t>(P, 64, planes, ah, 40 * 1024, stream, G);
   if (rc != AA_ERR_UNSUPPORTED) return rc;
-  rc = launch_ty<KH, KW, VR, false, in_t>(P, 32, planes, ah, 72 * 1024, stream);
+  rc = launch_ty<KH, KW, VR, false, in_t>(P, 32, planes, ah, 72 * 1024, stream, G);
   if (rc != AA_ERR_UNSUPPORTED) return rc;
-  return launch_ty<KH, KW, VR, false, in_t>(P, 16, planes, ah, 72 * 1024, stream);
+  return launch_ty<KH, KW, VR, false, in_t>(P, 16, planes, ah, 72 * 1024, stream, G);
 }
 
 template <int KH, int KW, typename in_t>
-int launch_k(TParams& P, int64_t planes, const BandedAxis& ah, int nc_max, cudaStream_t stream) {
+int launch_k(TParams& P, int64_t planes, const BandedAxis& ah, int nc_max, cudaStream_t stream, GeomPlan& G) {
   P.pcp = (nc_max + (KW - 1) * P.Ci + 3 + 3) & ~3;  // + up to 3 lead columns (aligned 16-byte copies); multiple of 4
   // 4 output rows per vertical step when every aligned group of 4 rows starts within 3 input rows and there
   // are enough taps to share (measured: +15-25 % for the bicubic gathers, -7 % for the 2-3 tap bilinear ones)
   if constexpr (KH >= 4) {
-    bool vr4 = true;
-    for (int64_t y = 0; y < P.out_h && vr4; y += 4)
-      vr4 = ah.h_start[std::min<int64_t>(P.out_h - 1, y + 3)] - ah.h_start[y] <= 3;
-    if (vr4) return launch_vr<KH, KW, 4, in_t>(P, planes, ah, stream);
+    bool vr4 = G.vr4 != 0;
+    if (!G.ty) {
+      vr4 = true;
+      for (int64_t y = 0; y < P.out_h && vr4; y += 4)
+        vr4 = ah.h_start[std::min<int64_t>(P.out_h - 1, y + 3)] - ah.h_start[y] <= 3;
+      G.vr4 = vr4 ? 1 : 0;
+    }
+    if (vr4) return launch_vr<KH, KW, 4, in_t>(P, planes, ah, stream, G);
   }
-  return launch_vr<KH, KW, 1, in_t>(P, planes, ah, stream);
+  return launch_vr<KH, KW, 1, in_t>(P, planes, ah, stream, G);
 }
 
 template <int KH, typename in_t>
-int launch_kh(TParams& P, int kw, int64_t nb, const BandedAxis& ah, int nc, cudaStream_t s) {
-  if (kw <= 2) return launch_k<KH, 2, in_t>(P, nb, ah, nc, s);
-  if (kw <= 3) return launch_k<KH, 3, in_t>(P, nb, ah, nc, s);
-  if (kw <= 5) return launch_k<KH, 5, in_t>(P, nb, ah, nc, s);
-  if (kw <= 7) return launch_k<KH, 7, in_t>(P, nb, ah, nc, s);
+int launch_kh(TParams& P, int kw, int64_t nb, const BandedAxis& ah, int nc, cudaStream_t s, GeomPlan& G) {
+  if (kw <= 2) return launch_k<KH, 2, in_t>(P, nb, ah, nc, s, G);
+  if (kw <= 3) return launch_k<KH, 3, in_t>(P, nb, ah, nc, s, G);
+  if (kw <= 5) return launch_k<KH, 5, in_t>(P, nb, ah, nc, s, G);
+  if (kw <= 7) return launch_k<KH, 7, in_t>(P, nb, ah, nc, s, G);
   return fail(AA_ERR_UNSUPPORTED, "tile: more than 7 horizontal taps");
 }
 
 template <typename in_t>
-int launch_in(TParams& P, int kh, int kw, int64_t nb, const BandedAxis& ah, int nc, cudaStream_t s) {
-  if (kh <= 2) return launch_kh<2, in_t>(P, kw, nb, ah, nc, s);
-  if (kh <= 3) return launch_kh<3, in_t>(P, kw, nb, ah, nc, s);
-  if (kh <= 5) return launch_kh<5, in_t>(P, kw, nb, ah, nc, s);
-  if (kh <= 7) return launch_kh<7, in_t>(P, kw, nb, ah, nc, s);
+int launch_in(TParams& P, int kh, int kw, int64_t nb, const BandedAxis& ah, int nc, cudaStream_t s, GeomPlan& G) {
+  if (kh <= 2) return launch_kh<2, in_t>(P, kw, nb, ah, nc, s, G);
+  if (kh <= 3) return launch_kh<3, in_t>(P, kw, nb, ah, nc, s, G);
+  if (kh <= 5) return launch_kh<5, in_t>(P, kw, nb, ah, nc, s, G);
+  if (kh <= 7) return launch_kh<7, in_t>(P, kw, nb, ah, nc, s, G);
   return fail(AA_ERR_UNSUPPORTED, "tile: more than 7 vertical taps");
 }
 
+std::mutex g_geom_mu;
+std::map<GeomKey, GeomPlan> g_geom;
+
 }  // namespace
+
+bool geom_lookup(const GeomKey& k, GeomPlan* p) {
+  std::lock_guard<std::mutex> lock(g_geom_mu);
+  auto it = g_geom.find(k);
+  if (it == g_geom.end()) return false;
+  *p = it->second;
+  return true;
+}
+void geom_store(const GeomKey& k, const GeomPlan& p) {
+  std::lock_guard<std::mutex> lock(g_geom_mu);
+  if (g_geom.size() > 4096) g_geom.clear();
+  g_geom[k] = p;
+}
+cudaError_t ensure_smem_attr_impl(const void* kern, int device, size_t smem) {
+  if (smem <= 48 * 1024) return cudaSuccess;
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> have;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = have.find({kern, device});
+  if (it != have.end() && it->second >= smem) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) have[{kern, device}] = smem;
+  return e;
+}
+void tile_plan_clear() {
+  std::lock_guard<std::mutex> lock(g_geom_mu);
+  g_geom.clear();
+}
 
 int launch_tile(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout,
                 const BandedAxis& ah, const BandedAxis& aw, int kh_max, int kw_max, OutEpi epi, cudaStream_t stream) {
@@ -385,22 +429,38 @@ int launch_tile(const void* in, int in_dtype, const Layout& lin, void* out, cons
   P.w_start = aw.start; P.w_size = aw.size; P.w_w = (const float*)aw.w; P.w_pitch = aw.pitch;
   P.in_h = (int)ah.n_in; P.in_wf = (int)(aw.n_in * Ci); P.out_h = (int)ah.n_out; P.out_wf = (int)(aw.n_out * Ci);
   P.tiles_x = (P.out_wf + TXF - 1) / TXF;
-  // exact column plan from the host mirror of the table (the row plan depends on the tile height)
-  int64_t nc = 1;
-  for (int64_t f0 = 0; f0 < P.out_wf; f0 += TXF) {
-    const int64_t f1 = std::min<int64_t>(P.out_wf, f0 + TXF) - 1;
-    const int64_t x0 = f0 / Ci, x1 = f1 / Ci;
-    nc = std::max<int64_t>(nc, ((int64_t)aw.h_start[x1] + aw.h_size[x1] - aw.h_start[x0]) * Ci);
+  const GeomKey gkey{ah.id, aw.id, 1 | (Ci << 8) | (in_dtype << 24) | ((epi.generic() ? 1 : 0) << 28)};
+  GeomPlan G;
+  const bool planned = geom_lookup(gkey, &G);
+  if (planned && !G.ty) return fail(AA_ERR_UNSUPPORTED, "tile: input patch too large; use the streaming/general path");
+  int64_t nc = G.nc;
+  if (!planned) {
+    // exact column plan from the host mirror of the table (the row plan depends on the tile height)
+    nc = 1;
+    for (int64_t f0 = 0; f0 < P.out_wf; f0 += TXF) {
+      const int64_t f1 = std::min<int64_t>(P.out_wf, f0 + TXF) - 1;
+      const int64_t x0 = f0 / Ci, x1 = f1 / Ci;
+      nc = std::max<int64_t>(nc, ((int64_t)aw.h_start[x1] + aw.h_size[x1] - aw.h_start[x0]) * Ci);
+    }
+    G.nc = (int)std::min<int64_t>(nc, 1 << 30);
+    if (nc > 4096) {
+      geom_store(gkey, G);  // ty == 0: remembered as not eligible
+      return fail(AA_ERR_UNSUPPORTED, "tile: input patch too large; use the streaming/general path");
+    }
   }
-  if (nc > 4096) return fail(AA_ERR_UNSUPPORTED, "tile: input patch too large; use the streaming/general path");
   P.vec_load = in_dtype == AA_F32 && ((uintptr_t)in) % 16 == 0 && lin.stride_h % 4 == 0 && lin.stride_n % 4 == 0 &&
                (lin.Cp == 1 || lin.stride_p % 4 == 0);
   P.dci = FastDiv::make((uint32_t)Ci);
   P.dcp = FastDiv::make((uint32_t)(lin.Cp > 0 ? lin.Cp : 1));
   P.vec_store = (((uintptr_t)out) % (epi.kind == 1 ? 4 : 16) == 0) && (lout.stride_h % 4 == 0) && (lout.stride_n % 4 == 0) &&
                 (lout.Cp == 1 || lout.stride_p % 4 == 0);
-  if (in_dtype == AA_F32) return launch_in<float>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream);
-  return launch_in<uint8_t>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream);
+  const int rc = in_dtype == AA_F32 ? launch_in<float>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream, G)
+                                    : launch_in<uint8_t>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream, G);
+  if (!planned && (rc == AA_OK || rc == AA_ERR_UNSUPPORTED) && lin.planes > 0) {
+    if (rc == AA_ERR_UNSUPPORTED) G.ty = 0;
+    geom_store(gkey, G);
+  }
+  return rc;
 }
 
 }  // namespace aa

@@ -1,0 +1,590 @@
+// aa_vmma.cu -- K4: fused forward for uint8 inputs with the VERTICAL pass on the 5th-generation tensor
+// cores (tcgen05.mma kind::i8, accumulators in TMEM) and input tiles staged by TMA tensor copies.
+//
+// Same contract as the streaming kernel (aa_stream.cu): one launch replaces the two TensorIterator
+// passes + temp tensor of ti_separable_upsample_generic_Nd_kernel_impl
+// (/root/reference/step_two_dot_two/aa_interpolation_impl.h:628-683); every input byte is read from HBM
+// once, every output element written once.  Why a different engine for uint8: with 1-byte pixels the
+// FP32 pipes need >= 6 issue slots per input byte (unpack + A FMAs per element) while
+// HBM delivers a byte every ~0.11 issue slots, so the streaming kernel tops out near 0.3-0.6 of HBM peak on
+// wide-tap shapes (cfg3).  Here the per-byte work of the vertical pass costs NO issue slots:
+//
+//   * the vertical filter of a block of OYB = 32 output rows is a banded matrix: out_v[oy, x] =
+//     sum_y Wh[oy, y] * in[y, x] with y in a window of <= 32*KSTEPS input rows.  Written as a GEMM
+//     D[x, (limb, oy)] = sum_y A[x, y] * B[y, (limb, oy)] the data operand A is the raw uint8 image tile
+//     (128 flat columns x 32 rows per MMA, M-major = exactly how TMA lands it in shared memory with the
+//     128-byte swizzle) and B holds the fp32 weights of :194-281 quantised to 24-bit fixed point and
+//     split into three balanced base-256 digits (int8 "limbs"; aa_tables.cu).  uint8 x int8 products
+//     accumulate exactly in int32 in TMEM, so the vertical pass is exact up to the 2^-s weight
+//     quantisation (s = 22..30: <= 7e-5 on a 0..255 scale in the worst case, far inside the
+//     1e-3 + 1e-5*|x| contract and below the fp32 rounding of the reference's own pass);
+//   * four epilogue warp pairs read the accumulators (tcgen05.ld), rebuild fp32 from the three limbs with
+//     three integer adds + three FFMA2 per two values (magic-number int->float, no I2F), and store the
+//     vertically filtered rows TRANSPOSED ([flat column][32 output rows]) in shared memory;
+//   * the HORIZONTAL pass is the same pair-of-columns gather as aa_stream_common.cuh, but one 128-bit
+//     LDS now feeds four output rows (4x fewer shared-memory loads than the row-major buffer).
+//
+// Roles (320 threads, one CTA per SM, persistent over a contiguous range of work items):
+//   warp 0     TMA producer: cp.async.bulk.tensor (4-D map: flat x, y, channel plane, image) into a ring
+//              of 4 KB stages + one bulk copy of the item's weight limbs; mbarrier complete_tx
+//   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=96, K=32) per stage and
+//              tcgen05.commit to release stages / publish accumulators
+//   warps 2-9  epilogue + horizontal pass (named barrier 1)
+// Work item = (plane, column strip of <= 512 flat input columns, block of 32 output rows), ordered so that
+// consecutive items of a CTA share the strip and walk DOWN the image: the 2*support halo rows an item
+// shares with its predecessor were fetched by the same SM a few microseconds earlier and hit in L2.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include <map>
+#include <mutex>
+
+#include "aa_stream_common.cuh"
+
+namespace aa {
+using namespace stream_detail;
+namespace {
+
+constexpr int OYB = 32;                      // output rows per item
+constexpr int NLIMB = 3;                     // int8 digits per weight
+constexpr int UMMA_N = OYB * NLIMB;          // 96 accumulator columns per tile
+constexpr int TILE_M = 128;                  // flat input columns per tile (= TMEM lanes)
+constexpr int KSTEP = 32;                    // input rows per MMA (K of an 8-bit tcgen05.mma)
+constexpr int STAGE_BYTES = KSTEP * TILE_M;  // 4096
+constexpr int MAX_TILES = 4;                 // tiles per strip
+constexpr int VCOLS = MAX_TILES * TILE_M;    // 512 flat columns of vertically filtered data
+constexpr int VPITCH = OYB + 4;              // floats per column of V (pad: conflict-free 128-bit stores)
+constexpr int NACC = 4;                      // accumulator buffers in TMEM (128 columns each)
+constexpr int MAX_KSTEPS = 8;
+constexpr int NWC = 8, NTC = NWC * 32, NT = NTC + 64;
+constexpr int BAR_BYTES = 1024;
+constexpr int MAX_STAGES = 40;
+
+struct VParams {
+  SParams S;            // output, epilogue, horizontal tables and strip plan (strip_setup reads these)
+  const int8_t* bq;     // [n_oyb][ksteps*32][128] weight limbs, 128B-swizzled rows (aa_tables.cu)
+  const float* qmeta;   // {c0, c1, c2, K0}: fp32 = fma(m2, c2, fma(m1, c1, fma(m0, c0, K0)))
+  int ksteps, n_oyb, nstage, b_bytes, Cp_in;
+  int64_t total_items;
+  uint32_t idesc;       // tcgen05 instruction descriptor
+  uint64_t desc_tmpl;   // shared-memory matrix descriptor without the start address
+  int* dbg;             // device: [0] = first watchdog code (0 = none)
+  long long timeout_clk;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a wrong descriptor or a lost transaction must not hang the GPU.  After timeout_clk cycles the
+// waiter records `code` and raises the CTA-wide abort flag; every role then drains its loops without waiting
+// (results are garbage, the host reports AA_ERR_CUDA from the debug word).
+struct Watch {
+  volatile int* abort_flag;
+  int* dbg;
+  long long limit;
+};
+__device__ __forceinline__ bool mbar_wait(const Watch& w, uint32_t bar, uint32_t parity, int code) {
+  if (mbar_try(bar, parity)) return true;
+  const long long t0 = clock64();
+  for (int spin = 0;; spin++) {
+    if (mbar_try(bar, parity)) return true;
+    if ((spin & 63) == 63) {
+      if (*w.abort_flag) return false;
+      if (clock64() - t0 > w.limit) {
+        *w.abort_flag = 1;
+        atomicCAS(w.dbg, 0, code);
+        return false;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int c, int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(x), "r"(y), "r"(c), "r"(n)
+      : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct Item {
+  int64_t plane;
+  int strip, oyb, ox0, ox1, fl0, ntiles;
+};
+__device__ __forceinline__ void item_strip(const VParams& P, Item& it) {  // geometry of it.strip
+  it.ox0 = it.strip * P.S.strip_ox;
+  it.ox1 = min((int)P.S.oW, it.ox0 + P.S.strip_ox);
+  it.fl0 = (__ldg(P.S.xmin_w + it.ox0) * P.S.Ci) & ~(P.S.aln - 1);  // TMA: the box must start on a 16-byte boundary
+  const int fl_end = (__ldg(P.S.xmin_w + it.ox1 - 1) + __ldg(P.S.xsize_w + it.ox1 - 1)) * P.S.Ci;
+  it.ntiles = (fl_end - it.fl0 + TILE_M - 1) / TILE_M;
+}
+// items are numbered (plane, strip, oyb) with oyb fastest
+__device__ __forceinline__ Item item_first(const VParams& P, int64_t i) {
+  Item it;
+  const int64_t t = i / P.n_oyb;
+  it.oyb = (int)(i - t * P.n_oyb);
+  it.plane = t / P.S.n_strips;
+  it.strip = (int)(t - it.plane * P.S.n_strips);
+  item_strip(P, it);
+  return it;
+}
+__device__ __forceinline__ void item_next(const VParams& P, Item& it) {
+  if (++it.oyb < P.n_oyb) return;
+  it.oyb = 0;
+  if (++it.strip == P.S.n_strips) { it.strip = 0; it.plane++; }
+  item_strip(P, it);
+}
+
+// Horizontal pass over the transposed buffer V[flat column][VPITCH]: one work item = one pair of adjacent
+// output columns (one channel) x 4 output rows; the 4 rows of a tap arrive in one LDS.128.  Window bookkeeping
+// (Wp, pinfo) is the pair form of aa_stream_common.cuh::strip_setup; as there, a lane never reads a column
+// outside its own pair's windows (the pointer stops advancing, the weights past the window are zero padding).
+template <bool GEN>
+__device__ __forceinline__ void hphase_T(const VParams& P, const float* __restrict__ V, const float2* __restrict__ Wp,
+                                         const int4* __restrict__ pinfo, int64_t op_off, int npc, int tc, int oy0, int nrows) {
+  const int npc32 = (npc + 31) & ~31;
+  const int Ci = P.S.Ci;
+  const int64_t osh = P.S.lout.stride_h;
+  for (int it = tc; it < npc32 * (OYB / 4); it += NTC) {
+    const int g = it / npc32;  // warp-uniform
+    const int pc = it - g * npc32;
+    if (4 * g >= nrows) break;
+    const bool act = pc < npc;
+    const int4 pi = pinfo[act ? pc : 0];
+    const int len = act ? (pi.z & 0xffff) : 1;
+    const int lenm = __reduce_max_sync(0xffffffffu, len);
+    const float2* wr = Wp + pi.y;
+    const float* vp = V + pi.x * VPITCH + 4 * g;
+    float2 h0 = make_float2(0.f, 0.f), h1 = h0, h2 = h0, h3 = h0;
+#pragma unroll 4
+    for (int j = 0; j < lenm; j++) {
+      const float2 w2 = wr[j];
+      const float4 v = *reinterpret_cast<const float4*>(vp);
+      h0 = __ffma2_rn(make_float2(v.x, v.x), w2, h0);
+      h1 = __ffma2_rn(make_float2(v.y, v.y), w2, h1);
+      h2 = __ffma2_rn(make_float2(v.z, v.z), w2, h2);
+      h3 = __ffma2_rn(make_float2(v.w, v.w), w2, h3);
+      vp += (j + 1 < len) ? Ci * VPITCH : 0;
+    }
+    if (act) {
+      const int64_t dst = op_off + (int64_t)(oy0 + 4 * g) * osh + pi.w;
+      const bool hasb = ((pi.z >> 16) & 1) != 0;
+      const int c = pi.z >> 20, cstep = P.S.epi.colstep(Ci);
+      const float2 hh[4] = {h0, h1, h2, h3};
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        if (4 * g + r < nrows) {
+          aa_store<GEN>(P.S.out, dst + (int64_t)r * osh, hh[r].x, c, P.S.epi);
+          if (hasb) aa_store<GEN>(P.S.out, dst + (int64_t)r * osh + cstep, hh[r].y, c, P.S.epi);
+        }
+      }
+    }
+  }
+}
+
+template <bool GEN>
+__global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ CUtensorMap tmap, const VParams P) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // the 128-byte swizzle atoms need 1024-byte alignment
+  unsigned char* sm = smem_raw + (base - raw);
+  // layout: A ring [nstage][4096] | B [2][b_bytes] | V [VCOLS][VPITCH] f32 | barriers | Wp | pinfo
+  const uint32_t sA = base;
+  const uint32_t sB = sA + (uint32_t)P.nstage * STAGE_BYTES;
+  float* V = reinterpret_cast<float*>(sm + (size_t)P.nstage * STAGE_BYTES + 2 * (size_t)P.b_bytes);
+  unsigned char* bar_base = reinterpret_cast<unsigned char*>(V) + sizeof(float) * VCOLS * VPITCH;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bar_base);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * MAX_STAGES;
+  const uint32_t tfull0 = empty0 + 8 * MAX_STAGES, tempty0 = tfull0 + 8 * NACC;
+  const uint32_t bfull0 = tempty0 + 8 * NACC, bempty0 = bfull0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_base + 8 * (2 * MAX_STAGES + 2 * NACC + 4));
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  float2* Wp = reinterpret_cast<float2*>(bar_base + BAR_BYTES);
+  int4* pinfo = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(Wp) + P.S.wtab_bytes + 15) & ~(uintptr_t)15);
+
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  if (t == 0) {
+    for (int i = 0; i < P.nstage; i++) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    for (int i = 0; i < NACC; i++) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, NWC); }
+    for (int i = 0; i < 2; i++) { mbar_init(bfull0 + 8 * i, 1); mbar_init(bempty0 + 8 * i, 1); }
+    *abort_flag = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM by shared-memory footprint)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const Watch W{abort_flag, P.dbg, P.timeout_clk};
+
+  const int64_t i_begin = P.total_items * (int64_t)blockIdx.x / gridDim.x;
+  const int64_t i_end = P.total_items * (int64_t)(blockIdx.x + 1) / gridDim.x;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0, bslot = 0;
+      uint32_t phase = 0, bphase = 0;
+      bool ok = true;
+      Item it = item_first(P, i_begin);
+      for (int64_t i = i_begin; i < i_end && ok; i++, item_next(P, it)) {
+        ok = mbar_wait(W, bempty0 + 8 * bslot, bphase ^ 1, 1);
+        if (!ok) break;
+        mbar_expect_tx(bfull0 + 8 * bslot, (uint32_t)P.b_bytes);
+        bulk_g2s(sB + (uint32_t)bslot * P.b_bytes, P.bq + (size_t)it.oyb * P.b_bytes, (uint32_t)P.b_bytes, bfull0 + 8 * bslot);
+        if (++bslot == 2) { bslot = 0; bphase ^= 1; }
+        const int y0 = __ldg(P.S.xmin_h + it.oyb * OYB);
+        const int pc = (int)(it.plane % P.Cp_in), pn = (int)(it.plane / P.Cp_in);
+        for (int s = 0; s < it.ntiles && ok; s++) {
+          for (int ks = 0; ks < P.ksteps; ks++) {
+            ok = mbar_wait(W, empty0 + 8 * stage, phase ^ 1, 2);
+            if (!ok) break;
+            mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
+            tma_load_4d(sA + (uint32_t)stage * STAGE_BYTES, &tmap, full0 + 8 * stage, it.fl0 + s * TILE_M, y0 + ks * KSTEP, pc, pn);
+            if (++stage == P.nstage) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      int stage = 0, bslot = 0, acc = 0;
+      uint32_t phase = 0, bphase = 0, aphase = 0;
+      bool ok = true;
+      Item it = item_first(P, i_begin);
+      for (int64_t i = i_begin; i < i_end && ok; i++, item_next(P, it)) {
+        ok = mbar_wait(W, bfull0 + 8 * bslot, bphase, 3);
+        if (!ok) break;
+        const uint64_t bdesc0 = P.desc_tmpl | (uint64_t)(((sB + (uint32_t)bslot * P.b_bytes) >> 4) & 0x3FFFu);
+        for (int s = 0; s < it.ntiles && ok; s++) {
+          ok = mbar_wait(W, tempty0 + 8 * acc, aphase ^ 1, 4);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
+          for (int ks = 0; ks < P.ksteps; ks++) {
+            ok = mbar_wait(W, full0 + 8 * stage, phase, 5);
+            if (!ok) break;
+            tc_fence_after();
+            const uint64_t adesc = P.desc_tmpl | (uint64_t)(((sA + (uint32_t)stage * STAGE_BYTES) >> 4) & 0x3FFFu);
+            umma_i8(d_tmem, adesc, bdesc0 + (uint64_t)(ks * (STAGE_BYTES >> 4)), P.idesc, ks > 0 ? 1u : 0u);
+            umma_commit(empty0 + 8 * stage);  // the stage is free once this (and every earlier) MMA has read it
+            if (++stage == P.nstage) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(tfull0 + 8 * acc);
+          if (++acc == NACC) { acc = 0; aphase ^= 1; }
+        }
+        umma_commit(bempty0 + 8 * bslot);
+        if (++bslot == 2) { bslot = 0; bphase ^= 1; }
+      }
+    }
+  } else {
+    // =============================== epilogue + horizontal pass =============================
+    const int tc = t - 64;
+    const int q = warp & 3;          // TMEM lane quarter this warp may read (warp id mod 4)
+    const int half = (warp - 2) >> 2;  // which 16 of the 32 output rows
+    const float c0 = __ldg(P.qmeta + 0), c1 = __ldg(P.qmeta + 1), c2 = __ldg(P.qmeta + 2), k0 = __ldg(P.qmeta + 3);
+    int acc = 0;
+    uint32_t aphase = 0;
+    int cur_strip = -1, strip_fl0 = 0, strip_npc = 0;
+    bool ok = true;
+    Item it = item_first(P, i_begin);
+    for (int64_t i = i_begin; i < i_end; i++, item_next(P, it)) {
+      if (it.strip != cur_strip) {
+        consumer_sync();
+        strip_setup(P.S, tc, NTC, it.ox0, it.ox1, Wp, pinfo, &strip_fl0, &strip_npc);
+        cur_strip = it.strip;
+        consumer_sync();
+      }
+      for (int s = 0; s < it.ntiles; s++) {
+        if (ok) ok = mbar_wait(W, tfull0 + 8 * acc, aphase, 6);
+        ok = __all_sync(0xffffffffu, ok);  // the TMEM loads below are warp-collective
+        tc_fence_after();
+        if (ok) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + half * 16);
+          int l0[16], l1[16], l2[16];
+          tmem_ld16(taddr, l0);
+          tmem_ld16(taddr + OYB, l1);
+          tmem_ld16(taddr + 2 * OYB, l2);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8 * acc);  // accumulators are in registers: the MMA warp may reuse the buffer
+          float* vrow = V + (size_t)(s * TILE_M + q * 32 + lane) * VPITCH + half * 16;
+          const float2 c0v = make_float2(c0, c0), c1v = make_float2(c1, c1), c2v = make_float2(c2, c2), k0v = make_float2(k0, k0);
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            float o[4];
+#pragma unroll
+            for (int p = 0; p < 4; p += 2) {
+              // int -> float by the 1.5*2^23 magic (|limb sum| < 2^22); the bias is folded into k0 (see aa_tables.cu)
+              const float2 m0 = make_float2(__int_as_float(l0[e + p] + 0x4B400000), __int_as_float(l0[e + p + 1] + 0x4B400000));
+              const float2 m1 = make_float2(__int_as_float(l1[e + p] + 0x4B400000), __int_as_float(l1[e + p + 1] + 0x4B400000));
+              const float2 m2 = make_float2(__int_as_float(l2[e + p] + 0x4B400000), __int_as_float(l2[e + p + 1] + 0x4B400000));
+              float2 u = __ffma2_rn(m0, c0v, k0v);
+              u = __ffma2_rn(m1, c1v, u);
+              u = __ffma2_rn(m2, c2v, u);
+              o[p] = u.x;
+              o[p + 1] = u.y;
+            }
+            *reinterpret_cast<float4*>(vrow + e) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        if (++acc == NACC) { acc = 0; aphase ^= 1; }
+      }
+      consumer_sync();
+      const int64_t op = (it.plane / P.S.lout.Cp) * P.S.lout.stride_n + (it.plane % P.S.lout.Cp) * P.S.lout.stride_p;
+      const int nrows = min(OYB, (int)P.S.oH - it.oyb * OYB);
+      hphase_T<GEN>(P, V, Wp, pinfo, op, strip_npc, tc, it.oyb * OYB, nrows);
+      consumer_sync();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+struct VPlanKey {
+  uint64_t th, tw;
+  int Ci, gen;
+  bool operator<(const VPlanKey& o) const {
+    if (th != o.th) return th < o.th;
+    if (tw != o.tw) return tw < o.tw;
+    if (Ci != o.Ci) return Ci < o.Ci;
+    return gen < o.gen;
+  }
+};
+struct VPlan {
+  int n_strips, strip_ox, kp, wtab_bytes, nstage, sms;
+  size_t smem;
+};
+std::mutex g_vplan_mu;
+std::map<VPlanKey, VPlan> g_vplans;
+int* g_dbg[64] = {};
+
+int debug_env(const char* name, long long dflt, long long* out) {
+  const char* e = getenv(name);
+  *out = e ? strtoll(e, nullptr, 0) : dflt;
+  return e != nullptr;
+}
+
+}  // namespace
+
+void vmma_plan_clear() {
+  std::lock_guard<std::mutex> lock(g_vplan_mu);
+  g_vplans.clear();
+}
+
+// Polls the watchdog word of `device` (set by a kernel whose mbarrier wait timed out).  Called by tests and by the
+// host-buffer entry after its synchronisation point; costs one 4-byte D2H copy.
+int vmma_check_watchdog(int device) {
+  if (device < 0 || device >= 64 || !g_dbg[device]) return AA_OK;
+  int v = 0;
+  AA_CUDA_TRY(cudaMemcpy(&v, g_dbg[device], sizeof(int), cudaMemcpyDeviceToHost));
+  if (v != 0) {
+    int zero = 0;
+    cudaMemcpy(g_dbg[device], &zero, sizeof(int), cudaMemcpyHostToDevice);
+    return fail(AA_ERR_CUDA, "vmma: mbarrier wait timed out in the tensor-core kernel (watchdog code " + std::to_string(v) + ")");
+  }
+  return AA_OK;
+}
+
+static int vmma_prepare_device(int device) {
+  std::lock_guard<std::mutex> lock(g_vplan_mu);
+  if (device < 0 || device >= 64) return fail(AA_ERR_INVALID, "bad device ordinal");
+  if (!g_dbg[device]) {
+    int* d = nullptr;
+    AA_CUDA_TRY(cudaMalloc(&d, 4 * sizeof(int)));
+    AA_CUDA_TRY(cudaMemset(d, 0, 4 * sizeof(int)));
+    g_dbg[device] = d;
+  }
+  return AA_OK;
+}
+
+int vmma_warm(AxisTables* th, cudaStream_t stream) {
+  int rc = vmma_prepare_device(th->device);
+  if (rc != AA_OK) return rc;
+  return ensure_vq_tables(th, OYB, KSTEP, MAX_KSTEPS, stream);
+}
+
+int launch_vmma(const void* in, const Layout& lin, void* out, const Layout& lout, AxisTables* th, AxisTables* tw, int64_t H,
+                int64_t W, int64_t oH, int64_t oW, OutEpi epi, cudaStream_t stream) {
+  if (th->dtype != AA_F32 || tw->dtype != AA_F32) return fail(AA_ERR_UNSUPPORTED, "vmma: f32 tables only");
+  const int Ci = lin.Ci;
+  // TMA: 16-byte aligned base and strides (uint8: elements == bytes)
+  if (((uintptr_t)in) % 16 || lin.stride_h % 16 || (lin.planes > lin.Cp && lin.stride_n % 16) || (lin.Cp > 1 && lin.stride_p % 16))
+    return fail(AA_ERR_UNSUPPORTED, "vmma: input rows are not 16-byte aligned");
+  if (W * Ci >= (1ll << 31) || H >= (1ll << 31) || oH >= (1 << 24) || tw->K >= (1 << 16) || Ci > 2047)
+    return fail(AA_ERR_UNSUPPORTED, "vmma: size limits");
+  if (th->xsize_max > 128) return fail(AA_ERR_UNSUPPORTED, "vmma: vertical window too long for the int32 accumulators");
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(AA_ERR_UNSUPPORTED, "vmma: cuTensorMapEncodeTiled is not available");
+  int rc = ensure_vq_tables(th, OYB, KSTEP, MAX_KSTEPS, stream);
+  if (rc != AA_OK) return rc;
+
+  VParams P;
+  P.S = SParams();
+  P.S.in = in; P.S.out = out; P.S.epi = epi; P.S.lin = lin; P.S.lout = lout; P.S.Ci = Ci;
+  P.S.H = H; P.S.oH = oH; P.S.oW = oW;
+  P.S.xmin_h = th->xmin; P.S.xsize_h = th->xsize;
+  P.S.xmin_w = tw->xmin; P.S.xsize_w = tw->xsize; P.S.w_w = (const float*)tw->w; P.S.Kw = tw->K;
+  P.S.aln = 16; P.S.pairs = 1; P.S.pad = 0;
+  P.bq = th->vq; P.qmeta = th->vq_meta; P.ksteps = th->vq_ksteps; P.n_oyb = th->vq_noyb;
+  P.b_bytes = P.ksteps * STAGE_BYTES;
+  P.Cp_in = lin.Cp;
+
+  const bool gen = epi.generic();
+  const VPlanKey key{th->id, tw->id, Ci, gen ? 1 : 0};
+  VPlan pl;
+  bool have = false;
+  {
+    std::lock_guard<std::mutex> lock(g_vplan_mu);
+    auto itp = g_vplans.find(key);
+    if (itp != g_vplans.end()) { pl = itp->second; have = true; }
+  }
+  if (!have) {
+    const int32_t* xs = tw->h_xmin.data();
+    const int32_t* xz = tw->h_xsize.data();
+    const size_t fixed = (size_t)2 * P.b_bytes + sizeof(float) * VCOLS * VPITCH + BAR_BYTES + 1024 /*alignment slack*/;
+    const size_t cap_total = 227 * 1024;
+    int n_strips = 1, strip_ox = (int)oW, kp = 0, wtab = 0;
+    size_t tab_bytes = 0;
+    for (;; n_strips++) {
+      if (n_strips > oW) return fail(AA_ERR_UNSUPPORTED, "vmma: a single output column spans more than one strip");
+      strip_ox = (int)((oW + n_strips - 1) / n_strips);
+      bool ok = strip_ox <= 2048;
+      int shift = 0;
+      for (int64_t a = 0; ok && a < oW; a += strip_ox) {
+        const int64_t b = std::min<int64_t>(oW, a + strip_ox) - 1;
+        if (((int64_t)xs[b] + xz[b]) * Ci - (((int64_t)xs[a] * Ci) & ~15ll) > VCOLS) ok = false;
+        for (int64_t o = a; o + 1 <= b; o += 2) shift = std::max<int>(shift, xs[o + 1] - xs[o]);
+      }
+      if (ok) {
+        kp = (tw->K + shift) | 1;
+        const int np = (strip_ox + 1) / 2;
+        wtab = (int)((size_t)np * kp * sizeof(float2));
+        tab_bytes = (size_t)wtab + 16 + (size_t)np * Ci * sizeof(int4);
+        if (kp >= (1 << 16) || fixed + tab_bytes + 8 * STAGE_BYTES > cap_total) ok = false;
+      }
+      if (ok) break;
+    }
+    n_strips = (int)((oW + strip_ox - 1) / strip_ox);
+    int nstage = (int)((cap_total - fixed - tab_bytes) / STAGE_BYTES);
+    if (nstage > MAX_STAGES) nstage = MAX_STAGES;
+    if (nstage < 8) return fail(AA_ERR_UNSUPPORTED, "vmma: shared memory plan too large");
+    pl.n_strips = n_strips; pl.strip_ox = strip_ox; pl.kp = kp; pl.wtab_bytes = wtab; pl.nstage = nstage;
+    pl.smem = fixed + tab_bytes + (size_t)nstage * STAGE_BYTES;
+    AA_CUDA_TRY(cudaDeviceGetAttribute(&pl.sms, cudaDevAttrMultiProcessorCount, th->device));
+    if (gen) AA_CUDA_TRY(cudaFuncSetAttribute(aa_vmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap_total));
+    else AA_CUDA_TRY(cudaFuncSetAttribute(aa_vmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap_total));
+    if ((rc = vmma_prepare_device(th->device)) != AA_OK) return rc;
+    std::lock_guard<std::mutex> lock(g_vplan_mu);
+    if (g_vplans.size() > 4096) g_vplans.clear();
+    g_vplans[key] = pl;
+  }
+  P.S.n_strips = pl.n_strips; P.S.strip_ox = pl.strip_ox; P.S.kp = pl.kp; P.S.wtab_bytes = pl.wtab_bytes;
+  P.nstage = pl.nstage;
+  P.total_items = lin.planes * pl.n_strips * P.n_oyb;
+  P.dbg = g_dbg[th->device];
+
+  // tcgen05 descriptors.  Instruction: D = s32, A = u8 (the image tile), B = s8 (weight limbs), both operands
+  // MN-major (the contiguous dimension is M resp. N), M = 128, N = 96.  Shared-memory matrices: 128-byte swizzle,
+  // 8 K-rows of 128 bytes per atom -> stride between atoms along K (SBO) = 1024 bytes; one atom wide along M/N.
+  long long v;
+  P.idesc = (2u << 4) | (0u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(UMMA_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+  if (debug_env("AA_VMMA_IDESC", 0, &v)) P.idesc = (uint32_t)v;
+  long long lbo = STAGE_BYTES, sbo = 1024, lay = 2;
+  debug_env("AA_VMMA_LBO", lbo, &lbo);
+  debug_env("AA_VMMA_SBO", sbo, &sbo);
+  debug_env("AA_VMMA_LAYOUT", lay, &lay);
+  P.desc_tmpl = ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)lay << 61);
+  debug_env("AA_VMMA_TIMEOUT_MS", 2000, &v);
+  P.timeout_clk = v * 2000000ll;  // ~2 GHz
+
+  // 4-D tensor map over the uint8 input: {flat x (W*Ci bytes), y, channel plane, image}
+  CUtensorMap tmap;
+  const int64_t n_img = lin.planes / lin.Cp;
+  const cuuint64_t dims[4] = {(cuuint64_t)(W * Ci), (cuuint64_t)H, (cuuint64_t)lin.Cp, (cuuint64_t)n_img};
+  const cuuint64_t any16 = (cuuint64_t)lin.stride_h * (cuuint64_t)H;  // placeholder stride of a size-1 dimension
+  const cuuint64_t strides[3] = {(cuuint64_t)lin.stride_h, lin.Cp > 1 ? (cuuint64_t)lin.stride_p : any16,
+                                 n_img > 1 ? (cuuint64_t)lin.stride_n : any16};
+  const cuuint32_t box[4] = {TILE_M, KSTEP, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(in), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(AA_ERR_UNSUPPORTED, "vmma: cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")");
+
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(pl.sms, P.total_items));
+  if (gen) aa_vmma_kernel<true><<<(unsigned)grid, NT, pl.smem, stream>>>(tmap, P);
+  else aa_vmma_kernel<false><<<(unsigned)grid, NT, pl.smem, stream>>>(tmap, P);
+  AA_LAUNCH_CHECK("aa_vmma_kernel");
+  return AA_OK;
+}
+
+}  // namespace aa

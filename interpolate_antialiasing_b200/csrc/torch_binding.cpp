@@ -9,7 +9,13 @@
 // plus what the reference stubs out (test.py:111-116): cubic_backward, nearest_backward, and
 // linear_backward_nonaa (the reference's literal, non-antialiased backward arithmetic).
 //
-// Semantics kept: output_size = (oH, oW); scale is always in/out (scale_factors {});
+// Each forward/backward also takes an optional trailing `scale_factors` ([sh, sw]): the argument the reference's
+// ti_upsample_*2d_cpu accept (aa_interpolation_impl.h:735,740-742) but its shim never passes
+// (extension_interpolate.cpp:12).  With it, output_size may be None (= floor(in * scale), compute_output_size) and the
+// table scale becomes 1/scale_factor (area_pixel_compute_scale), i.e. F.interpolate(scale_factor=s,
+// recompute_scale_factor=False).
+//
+// Semantics kept: output_size = (oH, oW); scale is in/out unless scale_factors is given;
 // align_corners only changes the scale; 4-D input; empty batch allowed; memory format of the
 // result = input.suggest_memory_format() (aa_interpolation_impl.h:752) / grad_output's
 // (aa_interpolation_backward_impl.h:214); errors surface as RuntimeError.  Differences: tensors
@@ -51,9 +57,35 @@ void common_check(at::IntArrayRef input_size, at::IntArrayRef output_size) {
               ") output (H: ", output_size[0], ", W: ", output_size[1], ")");
 }
 
-at::Tensor forward_common(const at::Tensor& input, at::IntArrayRef output_size, bool align_corners, int filter, int64_t flags,
-                          bool out_u8 = false) {
+using OptSize = c10::optional<std::vector<int64_t>>;
+using OptScales = c10::optional<std::vector<double>>;
+
+// at::native::upsample::compute_output_size (ATen/native/UpSample.h): exactly one of output_size / scale_factors
+std::vector<int64_t> resolve_output_size(at::IntArrayRef input_size, const OptSize& output_size, const OptScales& scale_factors) {
+  const int64_t spatial = (int64_t)input_size.size() - 2;
+  if (output_size.has_value()) {
+    TORCH_CHECK(!scale_factors.has_value(), "Must specify exactly one of output_size and scale_factors");
+    TORCH_CHECK((int64_t)output_size->size() == spatial, "It is expected output_size equals to ", spatial, ", but got size ", output_size->size());
+    return *output_size;
+  }
+  TORCH_CHECK(scale_factors.has_value(), "Must specify exactly one of output_size and scale_factors");
+  TORCH_CHECK((int64_t)scale_factors->size() == spatial, "It is expected scale_factors equals to ", spatial, ", but got size ", scale_factors->size());
+  std::vector<int64_t> r;
+  for (int64_t i = 0; i < spatial; i++) r.push_back((int64_t)((double)input_size[i + 2] * (*scale_factors)[i]));
+  return r;
+}
+aa_scales to_scales(const OptScales& sf) {
+  aa_scales sc = {0.0, 0.0};
+  if (sf.has_value() && sf->size() == 2) { sc.scale_h = (*sf)[0]; sc.scale_w = (*sf)[1]; }
+  return sc;
+}
+
+at::Tensor forward_common(const at::Tensor& input, const OptSize& osize_opt, bool align_corners, int filter, int64_t flags,
+                          bool out_u8 = false, const OptScales& scale_factors = c10::nullopt) {
   TORCH_CHECK(input.is_cuda(), "aa_interp_b200: input must be a CUDA tensor (this build has no CPU fallback)");
+  TORCH_CHECK(input.dim() == 4, "It is expected input_size equals to 4, but got size ", input.dim());
+  const std::vector<int64_t> osize_v = resolve_output_size(input.sizes(), osize_opt, scale_factors);
+  const at::IntArrayRef output_size(osize_v);
   common_check(input.sizes(), output_size);
   // Allow for empty batch size but not other dimensions (aa_interpolation_impl.h:747-750)
   TORCH_CHECK(input.numel() != 0 || c10::multiply_integers(input.sizes().begin() + 1, input.sizes().end()),
@@ -68,14 +100,18 @@ at::Tensor forward_common(const at::Tensor& input, at::IntArrayRef output_size, 
   c10::cuda::CUDAGuard guard(x.device());
   auto stream = c10::cuda::getCurrentCUDAStream();
   aa_tensor_desc di = make_desc(x), dd = make_desc(out);
-  const int rc = aa_resize_forward(&di, &dd, filter, align_corners ? 1 : 0, (uint32_t)flags, stream.stream());
+  const aa_scales sc = to_scales(scale_factors);
+  const int rc = aa_resize_forward_sf(&di, &dd, filter, align_corners ? 1 : 0, &sc, (uint32_t)flags, stream.stream());
   TORCH_CHECK(rc == 0, "aa_resize_forward failed (", rc, "): ", aa_last_error());
   return out;
 }
 
-at::Tensor backward_common(const at::Tensor& grad_output, at::IntArrayRef output_size, at::IntArrayRef input_size,
-                           bool align_corners, int filter, bool nonaa) {
+at::Tensor backward_common(const at::Tensor& grad_output, const OptSize& osize_opt, at::IntArrayRef input_size,
+                           bool align_corners, int filter, bool nonaa, const OptScales& scale_factors = c10::nullopt) {
   TORCH_CHECK(grad_output.is_cuda(), "aa_interp_b200: grad_output must be a CUDA tensor (no CPU fallback)");
+  TORCH_CHECK(input_size.size() == 4, "It is expected input_size equals to 4, but got size ", input_size.size());
+  const std::vector<int64_t> osize_v = resolve_output_size(input_size, osize_opt, scale_factors);
+  const at::IntArrayRef output_size(osize_v);
   common_check(input_size, output_size);
   // same checks as ti_upsample_bilinear2d_backward_cpu, aa_interpolation_backward_impl.h:201-212
   TORCH_CHECK(grad_output.dim() == 4, "Expected grad_output to be a tensor of dimension 4 but got: dimension ", grad_output.dim());
@@ -91,44 +127,67 @@ at::Tensor backward_common(const at::Tensor& grad_output, at::IntArrayRef output
   c10::cuda::CUDAGuard guard(g.device());
   auto stream = c10::cuda::getCurrentCUDAStream();
   aa_tensor_desc dg = make_desc(g), di = make_desc(gin);
+  const aa_scales sc = to_scales(scale_factors);
   const int rc = nonaa ? aa_resize_backward_nonaa_bilinear(&dg, &di, align_corners ? 1 : 0, stream.stream())
-                       : aa_resize_backward(&dg, &di, filter, align_corners ? 1 : 0, 0u, stream.stream());
+                       : aa_resize_backward_sf(&dg, &di, filter, align_corners ? 1 : 0, &sc, 0u, stream.stream());
   TORCH_CHECK(rc == 0, "aa_resize_backward failed (", rc, "): ", aa_last_error());
   return gin;
 }
 
-at::Tensor linear_forward(const at::Tensor& i, at::IntArrayRef o, bool a) { return forward_common(i, o, a, AA_FILTER_TRIANGLE, 0); }
-at::Tensor cubic_forward(const at::Tensor& i, at::IntArrayRef o, bool a) { return forward_common(i, o, a, AA_FILTER_CUBIC, 0); }
-at::Tensor nearest_forward(const at::Tensor& i, at::IntArrayRef o, bool a) { return forward_common(i, o, a, AA_FILTER_BOX, 0); }
+at::Tensor linear_forward(const at::Tensor& i, const OptSize& o, bool a, const OptScales& sf) {
+  return forward_common(i, o, a, AA_FILTER_TRIANGLE, 0, false, sf);
+}
+at::Tensor cubic_forward(const at::Tensor& i, const OptSize& o, bool a, const OptScales& sf) {
+  return forward_common(i, o, a, AA_FILTER_CUBIC, 0, false, sf);
+}
+// The box filter keeps the input dtype for uint8, as the reference's code intends (output = at::empty({0},
+// input.options()), aa_interpolation_impl.h:764; uint8 dispatch :566-570, :615-619): the float sum is truncated to
+// uint8 like the C++ store `*(scalar_t*)dst = ...`.  (As built against torch 2.11 the reference itself never gets
+// there: compute_indices_weights overwrites interp_size (:210) before the `interp_size > 1` test of :608, so its uint8
+// call raises "not implemented for 'Byte'" -- pinned in tests/test_oracle.py.)
+at::Tensor nearest_forward(const at::Tensor& i, const OptSize& o, bool a, const OptScales& sf) {
+  return forward_common(i, o, a, AA_FILTER_BOX, 0, /*out_u8=*/i.scalar_type() == at::kByte, sf);
+}
 at::Tensor forward_with_flags(const at::Tensor& i, at::IntArrayRef o, bool a, int64_t filter, int64_t flags) {
-  return forward_common(i, o, a, (int)filter, flags);
+  return forward_common(i, o.vec(), a, (int)filter, flags);
 }
 // fused epilogue: clamp to [0,255] + truncate (reference caller, test.py:71-75) or round to nearest -> uint8
 at::Tensor forward_u8(const at::Tensor& i, at::IntArrayRef o, bool a, int64_t filter, bool round_nearest) {
-  return forward_common(i, o, a, (int)filter, round_nearest ? AA_FLAG_ROUND_NEAREST : 0, /*out_u8=*/true);
+  return forward_common(i, o.vec(), a, (int)filter, round_nearest ? AA_FLAG_ROUND_NEAREST : 0, /*out_u8=*/true);
 }
-at::Tensor linear_backward(const at::Tensor& g, at::IntArrayRef o, at::IntArrayRef i, bool a) {
-  return backward_common(g, o, i, a, AA_FILTER_TRIANGLE, false);
+at::Tensor linear_backward(const at::Tensor& g, const OptSize& o, at::IntArrayRef i, bool a, const OptScales& sf) {
+  return backward_common(g, o, i, a, AA_FILTER_TRIANGLE, false, sf);
 }
-at::Tensor cubic_backward(const at::Tensor& g, at::IntArrayRef o, at::IntArrayRef i, bool a) {
-  return backward_common(g, o, i, a, AA_FILTER_CUBIC, false);
+at::Tensor cubic_backward(const at::Tensor& g, const OptSize& o, at::IntArrayRef i, bool a, const OptScales& sf) {
+  return backward_common(g, o, i, a, AA_FILTER_CUBIC, false, sf);
 }
-at::Tensor nearest_backward(const at::Tensor& g, at::IntArrayRef o, at::IntArrayRef i, bool a) {
-  return backward_common(g, o, i, a, AA_FILTER_BOX, false);
+at::Tensor nearest_backward(const at::Tensor& g, const OptSize& o, at::IntArrayRef i, bool a, const OptScales& sf) {
+  return backward_common(g, o, i, a, AA_FILTER_BOX, false, sf);
 }
 at::Tensor linear_backward_nonaa(const at::Tensor& g, at::IntArrayRef o, at::IntArrayRef i, bool a) {
-  return backward_common(g, o, i, a, AA_FILTER_TRIANGLE, true);
+  return backward_common(g, o.vec(), i, a, AA_FILTER_TRIANGLE, true);
 }
 
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
-  m.def("linear_forward", &linear_forward, "Anti-Aliased Linear Interpolation forward (sm_100a)");
-  m.def("nearest_forward", &nearest_forward, "Anti-Aliased box ('nearest') Interpolation forward (sm_100a)");
-  m.def("cubic_forward", &cubic_forward, "Anti-Aliased Cubic Interpolation forward (sm_100a)");
-  m.def("linear_backward", &linear_backward, "Anti-Aliased Linear Interpolation backward: true adjoint (sm_100a)");
-  m.def("cubic_backward", &cubic_backward, "Anti-Aliased Cubic Interpolation backward: true adjoint (sm_100a)");
-  m.def("nearest_backward", &nearest_backward, "Anti-Aliased box Interpolation backward: true adjoint (sm_100a)");
+  namespace py = pybind11;
+  // positional (input, output_size, align_corners) exactly as the reference; scale_factors is an optional extra
+  m.def("linear_forward", &linear_forward, "Anti-Aliased Linear Interpolation forward (sm_100a)", py::arg("input"),
+        py::arg("output_size"), py::arg("align_corners") = false, py::arg("scale_factors") = py::none());
+  m.def("nearest_forward", &nearest_forward, "Anti-Aliased box ('nearest') Interpolation forward (sm_100a)", py::arg("input"),
+        py::arg("output_size"), py::arg("align_corners") = false, py::arg("scale_factors") = py::none());
+  m.def("cubic_forward", &cubic_forward, "Anti-Aliased Cubic Interpolation forward (sm_100a)", py::arg("input"),
+        py::arg("output_size"), py::arg("align_corners") = false, py::arg("scale_factors") = py::none());
+  m.def("linear_backward", &linear_backward, "Anti-Aliased Linear Interpolation backward: true adjoint (sm_100a)",
+        py::arg("grad_output"), py::arg("output_size"), py::arg("input_size"), py::arg("align_corners") = false,
+        py::arg("scale_factors") = py::none());
+  m.def("cubic_backward", &cubic_backward, "Anti-Aliased Cubic Interpolation backward: true adjoint (sm_100a)",
+        py::arg("grad_output"), py::arg("output_size"), py::arg("input_size"), py::arg("align_corners") = false,
+        py::arg("scale_factors") = py::none());
+  m.def("nearest_backward", &nearest_backward, "Anti-Aliased box Interpolation backward: true adjoint (sm_100a)",
+        py::arg("grad_output"), py::arg("output_size"), py::arg("input_size"), py::arg("align_corners") = false,
+        py::arg("scale_factors") = py::none());
   m.def("linear_backward_nonaa", &linear_backward_nonaa, "The reference's literal (non-antialiased) linear backward");
   m.def("forward_with_flags", &forward_with_flags, "forward(input, output_size, align_corners, filter, AA_FLAG_*)");
   m.def("forward_u8", &forward_u8, "forward(input, output_size, align_corners, filter, round_nearest) -> uint8 (fused clamp + round)");

@@ -30,10 +30,20 @@ static int base_interp_size(int filter) { /* :287, :333, :377 */
 
 /* ------------------------------------------------------------------ fp32 instantiation ---- */
 
-/* torch ATen/native/UpSample.h area_pixel_compute_scale<float> (called at :314, :347, :391);
- * scale_factors is always {} (extension_interpolate.cpp:12) so the in/out branch is taken. */
+/* Optional caller-provided scale factors: the `scale_factors` argument of ti_upsample_*2d_cpu
+ * (:735, :740-742: get_scale_value), consumed by compute_scales_value in torch ATen/native/UpSample.h:
+ * (scale.has_value() && scale.value() > 0.) ? static_cast<T>(1.0 / scale.value()) : T(in) / out.
+ * The reference's shim always passes {} (extension_interpolate.cpp:12); the oracle keeps the knob so the
+ * product's scale_factors plumbing has something to be checked against.  Not thread-safe (test code). */
+static double g_sf_h = 0.0, g_sf_w = 0.0; /* per-call factors for forward/backward */
+static double g_axis_sf = 0.0;            /* factor of the axis whose tables are being built */
+void aa_oracle_set_scale_factors(double sh, double sw) { g_sf_h = sh; g_sf_w = sw; }
+void aa_oracle_set_axis_scale(double s) { g_axis_sf = s; }
+
+/* torch ATen/native/UpSample.h area_pixel_compute_scale<float> (called at :314, :347, :391) */
 static float scale_f32(int64_t in, int64_t out, int align) {
   if (align) return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.0f;
+  if (g_axis_sf > 0.) return (float)(1.0 / g_axis_sf);
   return (float)in / (float)out;
 }
 
@@ -117,6 +127,7 @@ int aa_oracle_tables_f32(int64_t in, int64_t out, int filter, int align,
 
 static double scale_f64(int64_t in, int64_t out, int align) {
   if (align) return out > 1 ? (double)(in - 1) / (double)(out - 1) : 0.0;
+  if (g_axis_sf > 0.) return 1.0 / g_axis_sf;
   return (double)in / (double)out;
 }
 static double filt_f64(int filter, double x) {
@@ -178,7 +189,11 @@ int aa_oracle_tables_f64(int64_t in, int64_t out, int filter, int align,
            int64_t ish, int64_t isw, T* out, int64_t oH, int64_t oW, int64_t osn, int64_t osc,       \
            int64_t osh, int64_t osw, int filter, int align) {                                        \
     if (N == 0) return 0;                                                                            \
-    int64_t kw_ = KFN(W, oW, filter, align), kh_ = KFN(H, oH, filter, align);                        \
+    g_axis_sf = g_sf_w;                                                                              \
+    int64_t kw_ = KFN(W, oW, filter, align);                                                         \
+    g_axis_sf = g_sf_h;                                                                              \
+    int64_t kh_ = KFN(H, oH, filter, align);                                                         \
+    g_axis_sf = 0.0;                                                                                 \
     int64_t* xminw = malloc(sizeof(int64_t) * oW);                                                   \
     int64_t* xsizew = malloc(sizeof(int64_t) * oW);                                                  \
     int64_t* xminh = malloc(sizeof(int64_t) * oH);                                                   \
@@ -187,8 +202,11 @@ int aa_oracle_tables_f64(int64_t in, int64_t out, int filter, int align,
     T* wh = malloc(sizeof(T) * oH * kh_);                                                             \
     T* tmp = malloc(sizeof(T) * (size_t)H * oW);                                                     \
     if (!xminw || !xsizew || !xminh || !xsizeh || !ww || !wh || !tmp) return -1;                     \
+    g_axis_sf = g_sf_w;                                                                              \
     int Kw = TABLES(W, oW, filter, align, xminw, xsizew, ww);                                        \
+    g_axis_sf = g_sf_h;                                                                              \
     int Kh = TABLES(H, oH, filter, align, xminh, xsizeh, wh);                                        \
+    g_axis_sf = 0.0;                                                                                 \
     for (int64_t n = 0; n < N; n++)                                                                  \
       for (int64_t c = 0; c < C; c++) {                                                              \
         const T* ip = in + n * isn + c * isc;                                                        \
@@ -280,7 +298,11 @@ DEFINE_NONAA_BACKWARD(aa_oracle_backward_nonaa_f64, double)
 #define DEFINE_ADJOINT(NAME, T, TABLES, KFN)                                                            \
   int NAME(const T* gout, int64_t planes, int64_t oH, int64_t oW, T* gin, int64_t H, int64_t W,      \
            int filter, int align) {                                                                  \
-    int64_t kw_ = KFN(W, oW, filter, align), kh_ = KFN(H, oH, filter, align);                        \
+    g_axis_sf = g_sf_w;                                                                              \
+    int64_t kw_ = KFN(W, oW, filter, align);                                                         \
+    g_axis_sf = g_sf_h;                                                                              \
+    int64_t kh_ = KFN(H, oH, filter, align);                                                         \
+    g_axis_sf = 0.0;                                                                                 \
     int64_t* xminw = malloc(sizeof(int64_t) * oW);                                                   \
     int64_t* xsizew = malloc(sizeof(int64_t) * oW);                                                  \
     int64_t* xminh = malloc(sizeof(int64_t) * oH);                                                   \
@@ -289,8 +311,11 @@ DEFINE_NONAA_BACKWARD(aa_oracle_backward_nonaa_f64, double)
     T* wh = malloc(sizeof(T) * oH * kh_);                                                             \
     T* tmp = malloc(sizeof(T) * (size_t)H * oW);                                                     \
     if (!xminw || !xsizew || !xminh || !xsizeh || !ww || !wh || !tmp) return -1;                     \
+    g_axis_sf = g_sf_w;                                                                              \
     int Kw = TABLES(W, oW, filter, align, xminw, xsizew, ww);                                        \
+    g_axis_sf = g_sf_h;                                                                              \
     int Kh = TABLES(H, oH, filter, align, xminh, xsizeh, wh);                                        \
+    g_axis_sf = 0.0;                                                                                 \
     for (int64_t c = 0; c < planes; c++) {                                                           \
       const T* g = gout + c * oH * oW;                                                               \
       T* gi = gin + c * H * W;                                                                       \

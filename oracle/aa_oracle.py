@@ -39,6 +39,8 @@ def lib():
             getattr(L, f"aa_oracle_forward_{sfx}").argtypes = [vp] + [i64] * 8 + [vp] + [i64] * 6 + [i32, i32]
             getattr(L, f"aa_oracle_backward_nonaa_{sfx}").argtypes = [vp, i64, i64, i64, vp, i64, i64, i32]
             getattr(L, f"aa_oracle_backward_adjoint_{sfx}").argtypes = [vp, i64, i64, i64, vp, i64, i64, i32, i32]
+        L.aa_oracle_set_axis_scale.argtypes = [ctypes.c_double]
+        L.aa_oracle_set_scale_factors.argtypes = [ctypes.c_double, ctypes.c_double]
         _lib = L
     return _lib
 
@@ -57,19 +59,45 @@ def _f(filter):
     return FILTERS[filter] if isinstance(filter, str) else int(filter)
 
 
-def interp_size(in_size, out_size, filter, align_corners=False, dtype=np.float32):
-    return getattr(lib(), f"aa_oracle_interp_size_{_sfx(dtype)}")(in_size, out_size, _f(filter), int(align_corners))
+class _axis_scale:
+    """Context: the caller-provided scale factor of one axis (compute_scales_value), 0/None = not given."""
+
+    def __init__(self, s):
+        self.s = float(s or 0.0)
+
+    def __enter__(self):
+        lib().aa_oracle_set_axis_scale(ctypes.c_double(self.s))
+
+    def __exit__(self, *a):
+        lib().aa_oracle_set_axis_scale(ctypes.c_double(0.0))
 
 
-def tables(in_size, out_size, filter, align_corners=False, dtype=np.float32):
-    """-> (xmin int64[out], xsize int64[out], weights dtype[out, K])"""
+class _scale_factors:
+    def __init__(self, sf):
+        self.sf = (0.0, 0.0) if sf is None else (float(sf[0] or 0.0), float(sf[1] or 0.0))
+
+    def __enter__(self):
+        lib().aa_oracle_set_scale_factors(ctypes.c_double(self.sf[0]), ctypes.c_double(self.sf[1]))
+
+    def __exit__(self, *a):
+        lib().aa_oracle_set_scale_factors(ctypes.c_double(0.0), ctypes.c_double(0.0))
+
+
+def interp_size(in_size, out_size, filter, align_corners=False, dtype=np.float32, scale=None):
+    with _axis_scale(scale):
+        return getattr(lib(), f"aa_oracle_interp_size_{_sfx(dtype)}")(in_size, out_size, _f(filter), int(align_corners))
+
+
+def tables(in_size, out_size, filter, align_corners=False, dtype=np.float32, scale=None):
+    """-> (xmin int64[out], xsize int64[out], weights dtype[out, K]); scale = the axis' scale factor, if given"""
     dtype = np.dtype(dtype)
-    K = interp_size(in_size, out_size, filter, align_corners, dtype)
+    K = interp_size(in_size, out_size, filter, align_corners, dtype, scale)
     xmin = np.empty(out_size, np.int64)
     xsize = np.empty(out_size, np.int64)
     w = np.empty((out_size, K), dtype)
-    k2 = getattr(lib(), f"aa_oracle_tables_{_sfx(dtype)}")(
-        in_size, out_size, _f(filter), int(align_corners), xmin.ctypes.data, xsize.ctypes.data, w.ctypes.data)
+    with _axis_scale(scale):
+        k2 = getattr(lib(), f"aa_oracle_tables_{_sfx(dtype)}")(
+            in_size, out_size, _f(filter), int(align_corners), xmin.ctypes.data, xsize.ctypes.data, w.ctypes.data)
     assert k2 == K
     return xmin, xsize, w
 
@@ -83,7 +111,7 @@ def dense_matrix(in_size, out_size, filter, align_corners=False, dtype=np.float3
     return m
 
 
-def forward(x, output_size, filter, align_corners=False, channels_last_out=None):
+def forward(x, output_size, filter, align_corners=False, channels_last_out=None, scale_factors=None):
     """x: numpy [N,C,H,W] (any strides, float32/float64).  Output memory format follows the input
     (aa_interpolation_impl.h:752): channels_last strides in -> channels_last strides out."""
     x = np.asarray(x)
@@ -100,9 +128,10 @@ def forward(x, output_size, filter, align_corners=False, channels_last_out=None)
     else:
         out = np.empty((N, C, oH, oW), x.dtype)
     osn, osc, osh, osw = (s // es for s in out.strides)
-    rc = getattr(lib(), f"aa_oracle_forward_{_sfx(x.dtype)}")(
-        x.ctypes.data, N, C, H, W, isn, isc, ish, isw, out.ctypes.data, oH, oW, osn, osc, osh, osw,
-        _f(filter), int(align_corners))
+    with _scale_factors(scale_factors):
+        rc = getattr(lib(), f"aa_oracle_forward_{_sfx(x.dtype)}")(
+            x.ctypes.data, N, C, H, W, isn, isc, ish, isw, out.ctypes.data, oH, oW, osn, osc, osh, osw,
+            _f(filter), int(align_corners))
     assert rc == 0
     return out
 
@@ -119,13 +148,14 @@ def backward_nonaa(grad_out, input_size, align_corners=False):
     return gi
 
 
-def backward_adjoint(grad_out, input_size, filter, align_corners=False):
+def backward_adjoint(grad_out, input_size, filter, align_corners=False, scale_factors=None):
     """True adjoint of forward(): Wh^T g Ww from the bit-exact tables."""
     g = np.ascontiguousarray(grad_out)
     N, C, oH, oW = g.shape
     H, W = int(input_size[-2]), int(input_size[-1])
     gi = np.empty((N, C, H, W), g.dtype)
-    rc = getattr(lib(), f"aa_oracle_backward_adjoint_{_sfx(g.dtype)}")(
-        g.ctypes.data, N * C, oH, oW, gi.ctypes.data, H, W, _f(filter), int(align_corners))
+    with _scale_factors(scale_factors):
+        rc = getattr(lib(), f"aa_oracle_backward_adjoint_{_sfx(g.dtype)}")(
+            g.ctypes.data, N * C, oH, oW, gi.ctypes.data, H, W, _f(filter), int(align_corners))
     assert rc == 0
     return gi

@@ -28,7 +28,7 @@ def test_header_symbols_exported():
     assert set(names) == set(capi.EXPORTS)
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/aa_resize.h but not exported"
-    assert L.aa_abi_version() == 1
+    assert L.aa_abi_version() == 2
 
 
 def test_no_oracle_in_product_path():
@@ -52,6 +52,23 @@ def test_interp_size_matches_oracle():
         align = rnd.random() < 0.5
         assert capi.interp_size(a, b, mode, align, capi.F32) == O.interp_size(a, b, mode, align, np.float32)
         assert capi.interp_size(a, b, mode, align, capi.F64) == O.interp_size(a, b, mode, align, np.float64)
+
+
+def test_host_tables_match_oracle():
+    """The host-side integer tables the launch planners use (aa_host_tables) are bit-identical to the oracle's
+    restatement of aa_interpolation_impl.h:253-257, with and without a caller-provided scale factor."""
+    from interpolate_antialiasing_b200 import capi
+    rnd = random.Random(11)
+    cases = [(906, 320), (438, 196), (1920, 224), (1080, 224), (3840, 512), (2160, 512), (512, 128), (64, 10), (1, 1), (5, 1), (1, 7)]
+    cases += [(rnd.randint(1, 4000), rnd.randint(1, 3000)) for _ in range(300)]
+    for a, b in cases:
+        mode = rnd.choice(["linear", "cubic", "nearest"])
+        align = rnd.random() < 0.3
+        for code, ndt in ((capi.F32, np.float32), (capi.F64, np.float64)):
+            for scale in (None, b / a * rnd.uniform(0.9, 1.1)):
+                xm, xs = capi.host_tables(a, b, mode, align, code, scale)
+                oxm, oxs, _ = O.tables(a, b, mode, align, ndt, scale)
+                assert np.array_equal(xm, oxm) and np.array_equal(xs, oxs), (a, b, mode, align, code, scale)
 
 
 def test_argument_errors_are_status_codes():

@@ -55,3 +55,22 @@ def test_interp_size_host_matches_oracle():
         align = rnd.random() < 0.5
         assert capi.interp_size(a, b, mode, align, capi.F32) == O.interp_size(a, b, mode, align, np.float32)
         assert capi.interp_size(a, b, mode, align, capi.F64) == O.interp_size(a, b, mode, align, np.float64)
+
+
+def test_device_tables_equal_host_tables_and_scale_factors(cuda):
+    """K1 (device) against the host-side integer tables used for launch planning, and both against the oracle, with the
+    reference's `scale_factors` knob (aa_interpolation_impl.h:735,740-742 -> area_pixel_compute_scale) exercised."""
+    from interpolate_antialiasing_b200 import capi
+    rnd = random.Random(21)
+    cases = [(1080, 224), (3840, 512), (512, 128), (128, 512), (97, 97)] + [(rnd.randint(1, 3000), rnd.randint(1, 2000)) for _ in range(60)]
+    for a, b in cases:
+        mode = rnd.choice(MODES)
+        tdt = rnd.choice([torch.float32, torch.float64])
+        ndt = np.float32 if tdt == torch.float32 else np.float64
+        for scale in (None, b / a * rnd.uniform(0.8, 1.25)):
+            xmin, xsize, w = capi.build_tables(a, b, mode, False, tdt, scale=scale)
+            hm, hs = capi.host_tables(a, b, mode, False, capi.F32 if tdt == torch.float32 else capi.F64, scale)
+            oxmin, oxsize, ow = O.tables(a, b, mode, False, ndt, scale)
+            assert np.array_equal(xmin.cpu().numpy(), hm) and np.array_equal(xsize.cpu().numpy(), hs), (a, b, mode, scale)
+            assert np.array_equal(hm, oxmin) and np.array_equal(hs, oxsize), (a, b, mode, scale)
+            assert np.array_equal(w.cpu().numpy(), ow), (a, b, mode, scale)
