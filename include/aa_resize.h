@@ -130,6 +130,15 @@ int aa_clear_table_cache(void);
  * the last call.  No reference counterpart (the reference is synchronous CPU code). */
 int aa_check_device(int device);
 
+/* Tuning aid for the tensor-core kernel (no reference counterpart): with AA_VMMA_PROF=1 in the environment every
+ * mbarrier wait adds the cycles it spent to a per-device counter (summed over the waiting warps):
+ *   [1] producer: weight-matrix slot free   [2] producer: stage free        [3] MMA: weights landed
+ *   [4] MMA: accumulator buffer released    [5] MMA: tile landed (TMA)      [6] epilogue: accumulators ready
+ *   [8] epilogue: barrier before the horizontal pass  [9] horizontal pass  [10] barrier after it
+ *   [12] producer warp lifetime  [13] MMA warp lifetime  [14] epilogue warps' lifetimes (sum of 8)
+ * Synchronise the stream first.  counters16: 16 x uint64 on the host. */
+int aa_debug_counters(int device, uint64_t* counters16, int reset);
+
 /* ---- the hot path --------------------------------------------------------------------------- */
 
 /* out[n,c,oy,ox] = sum_y sum_x Wh[oy,y] * Ww[ox,x] * in[n,c,y,x]   (horizontal then vertical in the
@@ -193,6 +202,14 @@ int aa_resize_backward_nonaa_bilinear(const aa_tensor_desc* grad_out, const aa_t
  * Pinned host memory is recommended (pageable works, slower). */
 int aa_resize_forward_host(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter,
                            int align_corners, uint32_t flags);
+
+/* One process, several GPUs: the batch is split by image into contiguous shards of
+ * ceil(n / n_devices), every device gets its own stream set, staging buffers and table-cache entries, all devices are
+ * enqueued before any is waited for, and the call returns after the last byte of `out` is written.  No collective: the
+ * shards are independent.  `devices` = CUDA ordinals (NULL / n_devices <= 0: every visible device); in->device is ignored.
+ * What a non-torch host binds to use the 8 B200s of a box from one thread; bit-identical to the single-device entry. */
+int aa_resize_forward_host_multi(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align_corners,
+                                 uint32_t flags, const int32_t* devices, int32_t n_devices);
 
 /* Number of this library's kernel launches issued by the calling thread since the last reset
  * (bench.py reports it as gpu_launches). */

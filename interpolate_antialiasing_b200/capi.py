@@ -17,8 +17,8 @@ FILTERS = {"nearest": BOX, "box": BOX, "bilinear": TRIANGLE, "linear": TRIANGLE,
 
 EXPORTS = [
     "aa_abi_version", "aa_last_error", "aa_interp_size", "aa_host_tables", "aa_build_tables", "aa_build_tables_sf", "aa_warm_tables",
-    "aa_clear_table_cache", "aa_check_device", "aa_resize_forward", "aa_resize_forward_sf", "aa_resize_backward_sf", "aa_resize_forward_ex", "aa_resize_backward",
-    "aa_resize_backward_nonaa_bilinear", "aa_resize_forward_host", "aa_launch_count",
+    "aa_clear_table_cache", "aa_check_device", "aa_debug_counters", "aa_resize_forward", "aa_resize_forward_sf", "aa_resize_backward_sf", "aa_resize_forward_ex", "aa_resize_backward",
+    "aa_resize_backward_nonaa_bilinear", "aa_resize_forward_host", "aa_resize_forward_host_multi", "aa_launch_count",
 ]
 
 
@@ -73,7 +73,9 @@ def lib():
         L.aa_resize_backward.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, u32, vp]
         L.aa_resize_backward_nonaa_bilinear.argtypes = [P(TensorDesc), P(TensorDesc), i32, vp]
         L.aa_resize_forward_host.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, u32]
+        L.aa_resize_forward_host_multi.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, u32, P(i32), i32]
         L.aa_check_device.argtypes = [i32]
+        L.aa_debug_counters.argtypes = [i32, vp, i32]
         L.aa_launch_count.argtypes = [i32]
         L.aa_launch_count.restype = i64
         _lib = L
@@ -182,11 +184,11 @@ def resize_forward_ex(x, output_size, filter, out, scale=None, bias=None, align_
     return out
 
 
-def resize_backward(grad_out, input_size, filter, align_corners=False, nonaa=False, flags=FLAG_AUTO, scales=None):
+def resize_backward(grad_out, input_size, filter, align_corners=False, nonaa=False, flags=FLAG_AUTO, scales=None, out=None):
     import torch
     cl = grad_out.is_contiguous(memory_format=torch.channels_last) and not grad_out.is_contiguous()
-    gin = torch.empty(tuple(input_size), dtype=grad_out.dtype, device=grad_out.device,
-                      memory_format=torch.channels_last if cl else torch.contiguous_format)
+    gin = out if out is not None else torch.empty(tuple(input_size), dtype=grad_out.dtype, device=grad_out.device,
+                                                  memory_format=torch.channels_last if cl else torch.contiguous_format)
     dg, di = desc(grad_out), desc(gin)
     if scales is not None:
         sc = Scales(float(scales[0] or 0.0), float(scales[1] or 0.0))
@@ -206,9 +208,28 @@ def resize_forward_host(x_host, out_host, filter, align_corners=False, flags=FLA
     return out_host
 
 
+def resize_forward_host_multi(x_host, out_host, filter, align_corners=False, flags=FLAG_AUTO, devices=None):
+    """One process, several GPUs: shards the host batch by image over `devices` (None: all visible) and returns when done."""
+    di, do = desc(x_host, 0), desc(out_host, 0)
+    if devices is None:
+        arr, n = None, 0
+    else:
+        n = len(devices)
+        arr = (ctypes.c_int32 * n)(*devices)
+    check(lib().aa_resize_forward_host_multi(ctypes.byref(di), ctypes.byref(do), _filter(filter), int(align_corners), flags, arr, n))
+    return out_host
+
+
 def check_device(device=0):
     """Raises if a kernel watchdog fired on `device` since the last call (call after torch.cuda.synchronize())."""
     check(lib().aa_check_device(device))
+
+
+def debug_counters(device=0, reset=True):
+    """AA_VMMA_PROF=1 wait-time counters of the tensor-core kernel (include/aa_resize.h: aa_debug_counters)."""
+    buf = (ctypes.c_uint64 * 16)()
+    check(lib().aa_debug_counters(device, ctypes.cast(buf, ctypes.c_void_p), int(reset)))
+    return list(buf)
 
 
 def launch_count(reset=False):

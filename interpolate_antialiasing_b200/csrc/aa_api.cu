@@ -303,6 +303,13 @@ int aa_check_device(int device) {
   return vmma_check_watchdog(device);
 }
 
+int aa_debug_counters(int device, uint64_t* counters16, int reset) {
+  if (!counters16) return fail(AA_ERR_INVALID, "aa_debug_counters: null destination");
+  DeviceGuard g(device);
+  if (!g.ok) return cuda_fail(g.err, "cudaSetDevice");
+  return vmma_read_counters(device, reinterpret_cast<unsigned long long*>(counters16), reset);
+}
+
 int aa_resize_forward(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align_corners, uint32_t flags,
                       void* cuda_stream) {
   return forward_impl(in, out, filter, align_corners, flags, (cudaStream_t)cuda_stream);
@@ -368,22 +375,21 @@ int aa_resize_backward_nonaa_bilinear(const aa_tensor_desc* gout, const aa_tenso
                                (cudaStream_t)cuda_stream);
 }
 
-// ---- host-buffer entry: chunked H2D -> resize -> D2H on rotating streams --------------------------
+// ---- host-buffer entries: chunked H2D -> resize -> D2H on rotating streams -------------------------
 namespace {
 struct HostCtx {
   static constexpr int NS = 3;
+  std::mutex mu;  // one host call at a time per device
   cudaStream_t streams[NS] = {};
   void* din[NS] = {};
   void* dout[NS] = {};
   size_t cap_in = 0, cap_out = 0;
   bool init = false;
 };
-std::mutex g_host_mu;
 HostCtx g_host_ctx[64];
-}  // namespace
 
 // dense NCHW (fmt 0) or NHWC (fmt 1) check for host buffers: the staging copies are flat memcpys
-static int dense_format(const aa_tensor_desc* t, int* fmt) {
+int dense_format(const aa_tensor_desc* t, int* fmt) {
   auto ok = [](int64_t size, int64_t stride, int64_t want) { return size == 1 || stride == want; };
   const bool cf = ok(t->w, t->stride_w, 1) && ok(t->h, t->stride_h, t->w) && ok(t->c, t->stride_c, t->h * t->w) &&
                   ok(t->n, t->stride_n, t->c * t->h * t->w);
@@ -393,49 +399,47 @@ static int dense_format(const aa_tensor_desc* t, int* fmt) {
   *fmt = (cf && cl) ? -1 : (cl ? 1 : 0);  // -1: both readings describe the same bytes
   return AA_OK;
 }
-static void dense_strides(aa_tensor_desc* t, int fmt) {
+void dense_strides(aa_tensor_desc* t, int fmt) {
   if (fmt == 1) { t->stride_c = 1; t->stride_w = t->c; t->stride_h = t->w * t->c; t->stride_n = t->h * t->w * t->c; }
   else { t->stride_w = 1; t->stride_h = t->w; t->stride_c = t->h * t->w; t->stride_n = t->c * t->h * t->w; }
 }
+size_t elem_size(int dtype) { return dtype == AA_U8 ? 1 : (dtype == AA_F32 ? 4 : 8); }
 
-int aa_resize_forward_host(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align_corners,
-                           uint32_t flags) {
+// Everything is validated BEFORE the first byte of the host buffers is touched.  -> memory format in *fmt
+int host_validate(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int* fmt) {
   int rc;
-  // everything is validated BEFORE the first byte of the host buffers is touched
   if ((rc = check_desc(in, "input")) != AA_OK) return rc;
   if ((rc = check_desc(out, "output")) != AA_OK) return rc;
   if ((rc = check_filter(filter)) != AA_OK) return rc;
   if (in->n != out->n || in->c != out->c) return fail(AA_ERR_INVALID, "input and output must agree in n and c");
   if (in->dtype > AA_F64) return fail(AA_ERR_INVALID, "input dtype must be u8, f32 or f64");
   if (out->dtype > AA_F64) return fail(AA_ERR_UNSUPPORTED, "host path: u8/f32/f64 outputs only");
-  {
-    const int tdtype = in->dtype == AA_F64 ? AA_F64 : AA_F32;
-    if (out->dtype != tdtype && !(out->dtype == AA_U8 && tdtype == AA_F32))
-      return fail(AA_ERR_INVALID, "output dtype must be f32 (or u8) for u8/f32 inputs and f64 for f64 inputs");
-  }
-  if (in->n == 0) return AA_OK;
-  const int dev = in->device;
-  if (dev < 0 || dev >= 64) return fail(AA_ERR_INVALID, "bad device ordinal");
+  const int tdtype = in->dtype == AA_F64 ? AA_F64 : AA_F32;
+  if (out->dtype != tdtype && !(out->dtype == AA_U8 && tdtype == AA_F32))
+    return fail(AA_ERR_INVALID, "output dtype must be f32 (or u8) for u8/f32 inputs and f64 for f64 inputs");
   int ifmt = 0, ofmt = 0;
   if (dense_format(in, &ifmt) != AA_OK || dense_format(out, &ofmt) != AA_OK)
     return fail(AA_ERR_UNSUPPORTED, "host path needs fully dense NCHW or NHWC buffers (no padded rows, slices or views)");
   if (ifmt >= 0 && ofmt >= 0 && ifmt != ofmt) return fail(AA_ERR_UNSUPPORTED, "input and output must use the same memory format");
-  const int fmt = ifmt >= 0 ? ifmt : (ofmt >= 0 ? ofmt : 0);
-  const size_t ies = in->dtype == AA_U8 ? 1 : (in->dtype == AA_F32 ? 4 : 8);
-  const size_t oes = out->dtype == AA_U8 ? 1 : (out->dtype == AA_F32 ? 4 : 8);
+  *fmt = ifmt >= 0 ? ifmt : (ofmt >= 0 ? ofmt : 0);
+  return AA_OK;
+}
+
+// Enqueues images [n0, n1) of the (validated) host batch on device `dev`'s rotating streams.  Caller holds C.mu and has
+// made `dev` current.  Nothing is synchronised here.
+int host_enqueue(const aa_tensor_desc* in, const aa_tensor_desc* out, int64_t n0, int64_t n1, int filter, int align, uint32_t flags,
+                 int fmt, int dev, HostCtx& C) {
+  const size_t ies = elem_size(in->dtype), oes = elem_size(out->dtype);
   const size_t img_in = (size_t)in->c * in->h * in->w, img_out = (size_t)out->c * out->h * out->w;
-  DeviceGuard g(dev);
-  if (!g.ok) return cuda_fail(g.err, "cudaSetDevice");
-  std::lock_guard<std::mutex> lock(g_host_mu);
-  HostCtx& C = g_host_ctx[dev];
   if (!C.init) {
     for (int i = 0; i < HostCtx::NS; i++) AA_CUDA_TRY(cudaStreamCreateWithFlags(&C.streams[i], cudaStreamNonBlocking));
     C.init = true;
   }
+  const int64_t n = n1 - n0;
   // chunk = as many images as fit ~96 MiB of input, at least 1, at most n/NS rounded up
   int64_t per = (int64_t)((96ull << 20) / (img_in * ies));
   if (per < 1) per = 1;
-  const int64_t even = (in->n + HostCtx::NS - 1) / HostCtx::NS;
+  const int64_t even = (n + HostCtx::NS - 1) / HostCtx::NS;
   if (per > even) per = even;
   const size_t need_in = (size_t)per * img_in * ies, need_out = (size_t)per * img_out * oes;
   if (need_in > C.cap_in || need_out > C.cap_out) {
@@ -455,28 +459,31 @@ int aa_resize_forward_host(const aa_tensor_desc* in, const aa_tensor_desc* out, 
   }
   // the staging buffers are dense by construction: their descs are rebuilt, never copied from the caller's strides
   aa_tensor_desc di = *in, dd_out = *out;
+  di.device = dd_out.device = dev;
   dense_strides(&di, fmt);
   dense_strides(&dd_out, fmt);
-  int64_t done = 0;
-  rc = AA_OK;
-  std::string err;
-  for (int i = 0; done < in->n && rc == AA_OK; i++) {
+  int64_t done = n0;
+  for (int i = 0; done < n1; i++) {
     const int s = i % HostCtx::NS;
-    const int64_t nb = std::min<int64_t>(per, in->n - done);
+    const int64_t nb = std::min<int64_t>(per, n1 - done);
     di.data = C.din[s]; di.n = nb;
     dd_out.data = C.dout[s]; dd_out.n = nb;
-    cudaError_t e = cudaMemcpyAsync(C.din[s], (const char*)in->data + (size_t)done * img_in * ies, (size_t)nb * img_in * ies,
-                                    cudaMemcpyHostToDevice, C.streams[s]);
-    if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(H2D)"); break; }
-    if ((rc = forward_impl(&di, &dd_out, filter, align_corners, flags, C.streams[s])) != AA_OK) break;
-    e = cudaMemcpyAsync((char*)out->data + (size_t)done * img_out * oes, C.dout[s], (size_t)nb * img_out * oes,
-                        cudaMemcpyDeviceToHost, C.streams[s]);
-    if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(D2H)"); break; }
+    AA_CUDA_TRY(cudaMemcpyAsync(C.din[s], (const char*)in->data + (size_t)done * img_in * ies, (size_t)nb * img_in * ies,
+                                cudaMemcpyHostToDevice, C.streams[s]));
+    int rc = forward_impl(&di, &dd_out, filter, align, flags, C.streams[s]);
+    if (rc != AA_OK) return rc;
+    AA_CUDA_TRY(cudaMemcpyAsync((char*)out->data + (size_t)done * img_out * oes, C.dout[s], (size_t)nb * img_out * oes,
+                                cudaMemcpyDeviceToHost, C.streams[s]));
     done += nb;
   }
-  if (rc != AA_OK) err = g_err;
-  // success or failure: nothing of this call may still be writing `out` (or reading `in`) when it returns
+  return AA_OK;
+}
+
+// Success or failure: nothing of the call may still be writing `out` (or reading `in`) when it returns.
+int host_drain(int dev, HostCtx& C, int rc) {
+  const std::string err = rc != AA_OK ? g_err : std::string();
   for (int i = 0; i < HostCtx::NS; i++) {
+    if (!C.streams[i]) continue;
     const cudaError_t e = cudaStreamSynchronize(C.streams[i]);
     if (e != cudaSuccess && rc == AA_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
   }
@@ -485,6 +492,71 @@ int aa_resize_forward_host(const aa_tensor_desc* in, const aa_tensor_desc* out, 
     return rc;
   }
   return vmma_check_watchdog(dev);
+}
+}  // namespace
+
+int aa_resize_forward_host(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align_corners,
+                           uint32_t flags) {
+  int rc, fmt = 0;
+  if ((rc = host_validate(in, out, filter, &fmt)) != AA_OK) return rc;
+  if (in->n == 0) return AA_OK;
+  const int dev = in->device;
+  if (dev < 0 || dev >= 64) return fail(AA_ERR_INVALID, "bad device ordinal");
+  DeviceGuard g(dev);
+  if (!g.ok) return cuda_fail(g.err, "cudaSetDevice");
+  HostCtx& C = g_host_ctx[dev];
+  std::lock_guard<std::mutex> lock(C.mu);
+  rc = host_enqueue(in, out, 0, in->n, filter, align_corners, flags, fmt, dev, C);
+  return host_drain(dev, C, rc);
+}
+
+int aa_resize_forward_host_multi(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align_corners,
+                                 uint32_t flags, const int32_t* devices, int32_t n_devices) {
+  int rc, fmt = 0;
+  if ((rc = host_validate(in, out, filter, &fmt)) != AA_OK) return rc;
+  int devs[64];
+  int nd = 0;
+  if (!devices || n_devices <= 0) {
+    int cnt = 0;
+    AA_CUDA_TRY(cudaGetDeviceCount(&cnt));
+    for (int i = 0; i < cnt && i < 64; i++) devs[nd++] = i;
+  } else {
+    if (n_devices > 64) return fail(AA_ERR_INVALID, "too many devices");
+    for (int i = 0; i < n_devices; i++) {
+      if (devices[i] < 0 || devices[i] >= 64) return fail(AA_ERR_INVALID, "bad device ordinal");
+      for (int j = 0; j < i; j++) if (devices[j] == devices[i]) return fail(AA_ERR_INVALID, "duplicate device ordinal");
+      devs[nd++] = devices[i];
+    }
+  }
+  if (nd == 0) return fail(AA_ERR_CUDA, "no CUDA device");
+  if (in->n == 0) return AA_OK;
+  // contiguous shards of ceil(n / devices) images; every device gets its own stream set, staging buffers
+  // and table cache entries; all devices are enqueued first, then all are drained
+  const int64_t per = (in->n + nd - 1) / nd;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  int first_rc = AA_OK;
+  std::string first_err;
+  int locked = 0;
+  for (int k = 0; k < nd; k++, locked++) {
+    g_host_ctx[devs[k]].mu.lock();
+    const int64_t n0 = std::min<int64_t>(in->n, per * k), n1 = std::min<int64_t>(in->n, per * (k + 1));
+    if (first_rc != AA_OK || n0 >= n1) continue;
+    cudaError_t e = cudaSetDevice(devs[k]);
+    rc = e == cudaSuccess ? host_enqueue(in, out, n0, n1, filter, align_corners, flags, fmt, devs[k], g_host_ctx[devs[k]])
+                          : cuda_fail(e, "cudaSetDevice");
+    if (rc != AA_OK) { first_rc = rc; first_err = g_err; }
+  }
+  for (int k = 0; k < locked; k++) {
+    if (cudaSetDevice(devs[k]) == cudaSuccess) {
+      rc = host_drain(devs[k], g_host_ctx[devs[k]], AA_OK);
+      if (rc != AA_OK && first_rc == AA_OK) { first_rc = rc; first_err = g_err; }
+    }
+    g_host_ctx[devs[k]].mu.unlock();
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  if (first_rc != AA_OK) g_err = first_err;
+  return first_rc;
 }
 
 }  // extern "C"

@@ -304,6 +304,7 @@ int launch_stream_adjoint(const void* gout, const Layout& lo, void* gin, const L
 int launch_vmma(const void* in, const Layout& lin, void* out, const Layout& lout, AxisTables* th, AxisTables* tw, int64_t H,
                 int64_t W, int64_t oH, int64_t oW, OutEpi epi, cudaStream_t stream);
 int vmma_check_watchdog(int device);
+int vmma_read_counters(int device, unsigned long long* out, int reset);
 int vmma_warm(AxisTables* th, cudaStream_t stream);  // everything a later launch_vmma would allocate or synchronise for
 void vmma_plan_clear();
 

@@ -24,12 +24,12 @@
 //   * the HORIZONTAL pass is the same pair-of-columns gather as aa_stream_common.cuh, but one 128-bit
 //     LDS now feeds four output rows (4x fewer shared-memory loads than the row-major buffer).
 //
-// Roles (320 threads, one CTA per SM, persistent over a contiguous range of work items):
+// Roles (576 threads, one CTA per SM, persistent over a contiguous range of work items):
 //   warp 0     TMA producer: cp.async.bulk.tensor (4-D map: flat x, y, channel plane, image) into a ring
 //              of 4 KB stages + one bulk copy of the item's weight limbs; mbarrier complete_tx
 //   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=96, K=32) per stage and
 //              tcgen05.commit to release stages / publish accumulators
-//   warps 2-9  epilogue + horizontal pass (named barrier 1)
+//   warps 2-17 epilogue + horizontal pass: 4 independent groups of 4 warps (one per TMEM lane quarter), 8 rows each
 // Work item = (plane, column strip of <= 512 flat input columns, block of 32 output rows), ordered so that
 // consecutive items of a CTA share the strip and walk DOWN the image: the 2*support halo rows an item
 // shares with its predecessor were fetched by the same SM a few microseconds earlier and hit in L2.
@@ -54,9 +54,12 @@ constexpr int STAGE_BYTES = KSTEP * TILE_M;  // 4096
 constexpr int MAX_TILES = 4;                 // tiles per strip
 constexpr int VCOLS = MAX_TILES * TILE_M;    // 512 flat columns of vertically filtered data
 constexpr int VPITCH = OYB + 4;              // floats per column of V (pad: conflict-free 128-bit stores)
+constexpr int VPADC = 32;                    // extra V columns a lane may read past its own window (zero weights, finite data)
+constexpr int VALLOC = VCOLS + VPADC;
 constexpr int NACC = 4;                      // accumulator buffers in TMEM (128 columns each)
 constexpr int MAX_KSTEPS = 8;
-constexpr int NWC = 8, NTC = NWC * 32, NT = NTC + 64;
+constexpr int NWC = 16, NTC = NWC * 32, NT = NTC + 64;  // 16 epilogue warps + producer + MMA issuer
+constexpr int NGRP = 4, GROWS = OYB / NGRP;             // 4 independent epilogue groups of 4 warps, 8 output rows each
 constexpr int BAR_BYTES = 1024;
 constexpr int MAX_STAGES = 40;
 
@@ -68,8 +71,10 @@ struct VParams {
   int64_t total_items;
   uint32_t idesc;       // tcgen05 instruction descriptor
   uint64_t desc_tmpl;   // shared-memory matrix descriptor without the start address
-  int* dbg;             // device: [0] = first watchdog code (0 = none)
+  int* dbg;             // device: [0] = first watchdog code (0 = none); 64-bit profile counters from byte 32
   long long timeout_clk;
+  int prof;
+  int hr;  // rows per thread in the horizontal pass (2, 4 or 8)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -92,12 +97,17 @@ struct Watch {
   volatile int* abort_flag;
   int* dbg;
   long long limit;
+  int prof;  // AA_VMMA_PROF=1: the cycles spent in each kind of wait are summed in `acc` and flushed once at kernel end
+  long long* acc;  // [16] per-thread accumulators (registers / local)
 };
 __device__ __forceinline__ bool mbar_wait(const Watch& w, uint32_t bar, uint32_t parity, int code) {
   if (mbar_try(bar, parity)) return true;
   const long long t0 = clock64();
   for (int spin = 0;; spin++) {
-    if (mbar_try(bar, parity)) return true;
+    if (mbar_try(bar, parity)) {
+      if (w.prof) w.acc[code] += clock64() - t0;
+      return true;
+    }
     if ((spin & 63) == 63) {
       if (*w.abort_flag) return false;
       if (clock64() - t0 > w.limit) {
@@ -125,7 +135,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(x), "r"(y), "r"(c), "r"(n)
       : "memory");
 }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory"); }
+// named barriers: 1 + g = the 128 threads of epilogue group g (they own rows [8g, 8g+8) of every item and run
+// independently of the other groups, so that one group's TMEM reads overlap another's shared-memory gather and the
+// schedulers always have several warps in different phases to pick from); 8 = all epilogue threads (strip changes only)
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(NTC / NGRP) : "memory"); }
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 8, %0;" ::"n"(NTC) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -146,6 +160,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16]) {
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -177,50 +197,75 @@ __device__ __forceinline__ void item_next(const VParams& P, Item& it) {
   item_strip(P, it);
 }
 
-// Horizontal pass over the transposed buffer V[flat column][VPITCH]: one work item = one pair of adjacent
-// output columns (one channel) x 4 output rows; the 4 rows of a tap arrive in one LDS.128.  Window bookkeeping
-// (Wp, pinfo) is the pair form of aa_stream_common.cuh::strip_setup; as there, a lane never reads a column
-// outside its own pair's windows (the pointer stops advancing, the weights past the window are zero padding).
-template <bool GEN>
+// Horizontal pass of one epilogue group over its 16 rows of the transposed buffer V[flat column][VPITCH]: one work
+// item = one pair of adjacent output columns (one channel) x R output rows (R = 8 or 4); the rows of a tap arrive in
+// R/4 LDS.128 and the pair's two weights in one LDS.64.  A warp covers 32*R/16 pairs x 16/R row chunks, so the weight
+// loads of the chunks coalesce and the V loads spread over all banks (pitch 36).  Window bookkeeping
+// (Wp, pinfo) is the pair form of aa_stream_common.cuh::strip_setup; as there, a lane never reads a column outside
+// its own pair's windows (the pointer stops advancing, the weights past the window are zero padding).
+template <bool GEN, int R, int CI>
 __device__ __forceinline__ void hphase_T(const VParams& P, const float* __restrict__ V, const float2* __restrict__ Wp,
-                                         const int4* __restrict__ pinfo, int64_t op_off, int npc, int tc, int oy0, int nrows) {
-  const int npc32 = (npc + 31) & ~31;
-  const int Ci = P.S.Ci;
+                                         const int4* __restrict__ pinfo, int64_t op_off, int npc, int tg, int grp, int oy0, int nrows) {
+  constexpr int NCH = GROWS / R;       // row chunks of the group's 8 rows
+  constexpr int PPW = 32 / NCH;        // pair-columns per warp iteration
+  constexpr int SH = R == 8 ? 5 : (R == 4 ? 4 : 3);   // log2(PPW)
+  const int Ci = CI ? CI : P.S.Ci;
   const int64_t osh = P.S.lout.stride_h;
-  for (int it = tc; it < npc32 * (OYB / 4); it += NTC) {
-    const int g = it / npc32;  // warp-uniform
-    const int pc = it - g * npc32;
-    if (4 * g >= nrows) break;
+  for (int it = tg; ((it >> 5) << SH) < npc; it += NTC / NGRP) {
+    const int pc = ((it >> 5) << SH) | (it & (PPW - 1));
+    const int r0 = grp * GROWS + ((it & 31) >> SH) * R;  // first of this thread's R rows inside the block
     const bool act = pc < npc;
     const int4 pi = pinfo[act ? pc : 0];
-    const int len = act ? (pi.z & 0xffff) : 1;
-    const int lenm = __reduce_max_sync(0xffffffffu, len);
+    // warp-uniform trip count = the longest union window of the warp's pairs.  A lane whose own window is shorter
+    // keeps walking: its weights there are the table's zero padding and V holds finite values everywhere (uint8 data,
+    // buffer zeroed at start; the host plan keeps pi.x + trip*Ci inside the VALLOC columns), so nothing leaks.
+    const int lenm = __reduce_max_sync(0xffffffffu, act ? (pi.z & 0xffff) : 1);
     const float2* wr = Wp + pi.y;
-    const float* vp = V + pi.x * VPITCH + 4 * g;
-    float2 h0 = make_float2(0.f, 0.f), h1 = h0, h2 = h0, h3 = h0;
+    const float* vp = V + pi.x * VPITCH + r0;
+    const int vstep = Ci * VPITCH;
+    float2 h[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) h[r] = make_float2(0.f, 0.f);
 #pragma unroll 4
     for (int j = 0; j < lenm; j++) {
       const float2 w2 = wr[j];
-      const float4 v = *reinterpret_cast<const float4*>(vp);
-      h0 = __ffma2_rn(make_float2(v.x, v.x), w2, h0);
-      h1 = __ffma2_rn(make_float2(v.y, v.y), w2, h1);
-      h2 = __ffma2_rn(make_float2(v.z, v.z), w2, h2);
-      h3 = __ffma2_rn(make_float2(v.w, v.w), w2, h3);
-      vp += (j + 1 < len) ? Ci * VPITCH : 0;
+      if constexpr (R >= 4) {
+#pragma unroll
+        for (int q = 0; q < R; q += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(vp + j * vstep + q);
+          h[q + 0] = __ffma2_rn(make_float2(v.x, v.x), w2, h[q + 0]);
+          h[q + 1] = __ffma2_rn(make_float2(v.y, v.y), w2, h[q + 1]);
+          h[q + 2] = __ffma2_rn(make_float2(v.z, v.z), w2, h[q + 2]);
+          h[q + 3] = __ffma2_rn(make_float2(v.w, v.w), w2, h[q + 3]);
+        }
+      } else {
+        const float2 v = *reinterpret_cast<const float2*>(vp + j * vstep);
+        h[0] = __ffma2_rn(make_float2(v.x, v.x), w2, h[0]);
+        h[1] = __ffma2_rn(make_float2(v.y, v.y), w2, h[1]);
+      }
     }
     if (act) {
-      const int64_t dst = op_off + (int64_t)(oy0 + 4 * g) * osh + pi.w;
+      const int64_t dst = op_off + (int64_t)(oy0 + r0) * osh + pi.w;
       const bool hasb = ((pi.z >> 16) & 1) != 0;
       const int c = pi.z >> 20, cstep = P.S.epi.colstep(Ci);
-      const float2 hh[4] = {h0, h1, h2, h3};
 #pragma unroll
-      for (int r = 0; r < 4; r++) {
-        if (4 * g + r < nrows) {
-          aa_store<GEN>(P.S.out, dst + (int64_t)r * osh, hh[r].x, c, P.S.epi);
-          if (hasb) aa_store<GEN>(P.S.out, dst + (int64_t)r * osh + cstep, hh[r].y, c, P.S.epi);
+      for (int r = 0; r < R; r++) {
+        if (r0 + r < nrows) {
+          aa_store<GEN>(P.S.out, dst + (int64_t)r * osh, h[r].x, c, P.S.epi);
+          if (hasb) aa_store<GEN>(P.S.out, dst + (int64_t)r * osh + cstep, h[r].y, c, P.S.epi);
         }
       }
     }
+  }
+}
+template <bool GEN, int R>
+__device__ __forceinline__ void hphase_ci(const VParams& P, const float* V, const float2* Wp, const int4* pinfo, int64_t op_off,
+                                          int npc, int tg, int grp, int oy0, int nrows) {
+  switch (P.S.Ci) {  // compile-time interleave: the tap offsets become immediates
+    case 1: hphase_T<GEN, R, 1>(P, V, Wp, pinfo, op_off, npc, tg, grp, oy0, nrows); break;
+    case 3: hphase_T<GEN, R, 3>(P, V, Wp, pinfo, op_off, npc, tg, grp, oy0, nrows); break;
+    case 4: hphase_T<GEN, R, 4>(P, V, Wp, pinfo, op_off, npc, tg, grp, oy0, nrows); break;
+    default: hphase_T<GEN, R, 0>(P, V, Wp, pinfo, op_off, npc, tg, grp, oy0, nrows); break;
   }
 }
 
@@ -230,11 +275,12 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // the 128-byte swizzle atoms need 1024-byte alignment
   unsigned char* sm = smem_raw + (base - raw);
-  // layout: A ring [nstage][4096] | B [2][b_bytes] | V [VCOLS][VPITCH] f32 | barriers | Wp | pinfo
+  // layout: A ring [nstage][b_bytes] (one stage = the whole K span of one tile) | B [2][b_bytes] | V [VCOLS][VPITCH] f32 |
+  //         barriers | Wp | pinfo
   const uint32_t sA = base;
-  const uint32_t sB = sA + (uint32_t)P.nstage * STAGE_BYTES;
-  float* V = reinterpret_cast<float*>(sm + (size_t)P.nstage * STAGE_BYTES + 2 * (size_t)P.b_bytes);
-  unsigned char* bar_base = reinterpret_cast<unsigned char*>(V) + sizeof(float) * VCOLS * VPITCH;
+  const uint32_t sB = sA + (uint32_t)P.nstage * (uint32_t)P.b_bytes;
+  float* V = reinterpret_cast<float*>(sm + ((size_t)P.nstage + 2) * (size_t)P.b_bytes);
+  unsigned char* bar_base = reinterpret_cast<unsigned char*>(V) + sizeof(float) * VALLOC * VPITCH;
   uint64_t* bars = reinterpret_cast<uint64_t*>(bar_base);
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * MAX_STAGES;
   const uint32_t tfull0 = empty0 + 8 * MAX_STAGES, tempty0 = tfull0 + 8 * NACC;
@@ -261,7 +307,14 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const Watch W{abort_flag, P.dbg, P.timeout_clk};
+  long long wacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const Watch W{abort_flag, P.dbg, P.timeout_clk, P.prof, wacc};
+  const long long t_kernel0 = clock64();
+  if (warp >= 2) {
+    // V: finite everywhere from the start (lanes may read zero-weight taps past their own window)
+    for (int i = t - 64; i < VALLOC * VPITCH / 4; i += NTC) reinterpret_cast<float4*>(V)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
 
   const int64_t i_begin = P.total_items * (int64_t)blockIdx.x / gridDim.x;
   const int64_t i_end = P.total_items * (int64_t)(blockIdx.x + 1) / gridDim.x;
@@ -281,14 +334,12 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
         if (++bslot == 2) { bslot = 0; bphase ^= 1; }
         const int y0 = __ldg(P.S.xmin_h + it.oyb * OYB);
         const int pc = (int)(it.plane % P.Cp_in), pn = (int)(it.plane / P.Cp_in);
-        for (int s = 0; s < it.ntiles && ok; s++) {
-          for (int ks = 0; ks < P.ksteps; ks++) {
-            ok = mbar_wait(W, empty0 + 8 * stage, phase ^ 1, 2);
-            if (!ok) break;
-            mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
-            tma_load_4d(sA + (uint32_t)stage * STAGE_BYTES, &tmap, full0 + 8 * stage, it.fl0 + s * TILE_M, y0 + ks * KSTEP, pc, pn);
-            if (++stage == P.nstage) { stage = 0; phase ^= 1; }
-          }
+        for (int s = 0; s < it.ntiles; s++) {  // one TMA box per tile: 128 flat columns x ksteps*32 rows
+          ok = mbar_wait(W, empty0 + 8 * stage, phase ^ 1, 2);
+          if (!ok) break;
+          mbar_expect_tx(full0 + 8 * stage, (uint32_t)P.b_bytes);
+          tma_load_4d(sA + (uint32_t)stage * P.b_bytes, &tmap, full0 + 8 * stage, it.fl0 + s * TILE_M, y0, pc, pn);
+          if (++stage == P.nstage) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -308,15 +359,14 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
           if (!ok) break;
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
-          for (int ks = 0; ks < P.ksteps; ks++) {
-            ok = mbar_wait(W, full0 + 8 * stage, phase, 5);
-            if (!ok) break;
-            tc_fence_after();
-            const uint64_t adesc = P.desc_tmpl | (uint64_t)(((sA + (uint32_t)stage * STAGE_BYTES) >> 4) & 0x3FFFu);
-            umma_i8(d_tmem, adesc, bdesc0 + (uint64_t)(ks * (STAGE_BYTES >> 4)), P.idesc, ks > 0 ? 1u : 0u);
-            umma_commit(empty0 + 8 * stage);  // the stage is free once this (and every earlier) MMA has read it
-            if (++stage == P.nstage) { stage = 0; phase ^= 1; }
-          }
+          ok = mbar_wait(W, full0 + 8 * stage, phase, 5);
+          if (!ok) break;
+          tc_fence_after();
+          const uint64_t adesc0 = P.desc_tmpl | (uint64_t)(((sA + (uint32_t)stage * P.b_bytes) >> 4) & 0x3FFFu);
+          for (int ks = 0; ks < P.ksteps; ks++)  // 32 rows (4096 bytes) of both operands per MMA
+            umma_i8(d_tmem, adesc0 + (uint64_t)(ks * (STAGE_BYTES >> 4)), bdesc0 + (uint64_t)(ks * (STAGE_BYTES >> 4)), P.idesc, ks > 0 ? 1u : 0u);
+          umma_commit(empty0 + 8 * stage);  // the stage is free once these MMAs have read it
+          if (++stage == P.nstage) { stage = 0; phase ^= 1; }
           umma_commit(tfull0 + 8 * acc);
           if (++acc == NACC) { acc = 0; aphase ^= 1; }
         }
@@ -328,7 +378,7 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
     // =============================== epilogue + horizontal pass =============================
     const int tc = t - 64;
     const int q = warp & 3;          // TMEM lane quarter this warp may read (warp id mod 4)
-    const int half = (warp - 2) >> 2;  // which 16 of the 32 output rows
+    const int half = (warp - 2) >> 2;  // epilogue group: which 8 of the 32 output rows
     const float c0 = __ldg(P.qmeta + 0), c1 = __ldg(P.qmeta + 1), c2 = __ldg(P.qmeta + 2), k0 = __ldg(P.qmeta + 3);
     int acc = 0;
     uint32_t aphase = 0;
@@ -347,23 +397,27 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
         ok = __all_sync(0xffffffffu, ok);  // the TMEM loads below are warp-collective
         tc_fence_after();
         if (ok) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + half * 16);
-          int l0[16], l1[16], l2[16];
-          tmem_ld16(taddr, l0);
-          tmem_ld16(taddr + OYB, l1);
-          tmem_ld16(taddr + 2 * OYB, l2);
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + half * GROWS);
+          int l0[GROWS], l1[GROWS], l2[GROWS];
+          const long long t_e0 = P.prof ? clock64() : 0;
+          tmem_ld8(taddr, l0);
+          tmem_ld8(taddr + OYB, l1);
+          tmem_ld8(taddr + 2 * OYB, l2);
           tmem_ld_wait();
+          if (P.prof) wacc[7] += clock64() - t_e0;  // TMEM read
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty0 + 8 * acc);  // accumulators are in registers: the MMA warp may reuse the buffer
-          float* vrow = V + (size_t)(s * TILE_M + q * 32 + lane) * VPITCH + half * 16;
+          float* vrow = V + (size_t)(s * TILE_M + q * 32 + lane) * VPITCH + half * GROWS;
           const float2 c0v = make_float2(c0, c0), c1v = make_float2(c1, c1), c2v = make_float2(c2, c2), k0v = make_float2(k0, k0);
 #pragma unroll
-          for (int e = 0; e < 16; e += 4) {
+          for (int e = 0; e < GROWS; e += 4) {
             float o[4];
 #pragma unroll
             for (int p = 0; p < 4; p += 2) {
-              // int -> float by the 1.5*2^23 magic (|limb sum| < 2^22); the bias is folded into k0 (see aa_tables.cu)
+              // int -> float by the 1.5*2^23 magic (|limb sum| < 2^22); the bias is folded into k0 (see aa_tables.cu).
+              // (Pre-arming the accumulators with the magic through tcgen05.st instead was measured slower: ptxas
+              // re-materialises the 16 constant source registers of every STTM.)
               const float2 m0 = make_float2(__int_as_float(l0[e + p] + 0x4B400000), __int_as_float(l0[e + p + 1] + 0x4B400000));
               const float2 m1 = make_float2(__int_as_float(l1[e + p] + 0x4B400000), __int_as_float(l1[e + p + 1] + 0x4B400000));
               const float2 m2 = make_float2(__int_as_float(l2[e + p] + 0x4B400000), __int_as_float(l2[e + p + 1] + 0x4B400000));
@@ -375,15 +429,34 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
             }
             *reinterpret_cast<float4*>(vrow + e) = make_float4(o[0], o[1], o[2], o[3]);
           }
+          if (P.prof) wacc[11] += clock64() - t_e0;  // whole epilogue of the tile (TMEM read + convert + store)
         }
         if (++acc == NACC) { acc = 0; aphase ^= 1; }
       }
-      consumer_sync();
+      const long long t_h0 = clock64();
+      group_sync(half);  // this group's 16 rows of all tiles are in V
+      const long long t_h1 = clock64();
       const int64_t op = (it.plane / P.S.lout.Cp) * P.S.lout.stride_n + (it.plane % P.S.lout.Cp) * P.S.lout.stride_p;
       const int nrows = min(OYB, (int)P.S.oH - it.oyb * OYB);
-      hphase_T<GEN>(P, V, Wp, pinfo, op, strip_npc, tc, it.oyb * OYB, nrows);
-      consumer_sync();
+      // rows per thread: the pass is bound by shared-memory bandwidth (2 B of V per FMA for a column pair + 4/R B of
+      // weights), so more rows per thread is less traffic; fewer rows only when the strip is too narrow to occupy the warps
+      if (P.hr == 8) hphase_ci<GEN, 8>(P, V, Wp, pinfo, op, strip_npc, tc & (NTC / NGRP - 1), half, it.oyb * OYB, nrows);
+      else if (P.hr == 4) hphase_ci<GEN, 4>(P, V, Wp, pinfo, op, strip_npc, tc & (NTC / NGRP - 1), half, it.oyb * OYB, nrows);
+      else hphase_ci<GEN, 2>(P, V, Wp, pinfo, op, strip_npc, tc & (NTC / NGRP - 1), half, it.oyb * OYB, nrows);
+      const long long t_h2 = clock64();
+      group_sync(half);  // V rows of this group may be overwritten
+      if (P.prof) {
+        wacc[8] += t_h1 - t_h0;        // barrier before the horizontal pass
+        wacc[9] += t_h2 - t_h1;        // horizontal pass
+        wacc[10] += clock64() - t_h2;  // barrier after it
+      }
     }
+  }
+  if (P.prof && lane == 0) {
+    unsigned long long* pc = reinterpret_cast<unsigned long long*>(P.dbg) + 4;
+    for (int k = 1; k < 12; k++)
+      if (wacc[k]) atomicAdd(pc + k, (unsigned long long)wacc[k]);
+    atomicAdd(pc + 12 + (warp == 0 ? 0 : warp == 1 ? 1 : 2), (unsigned long long)(clock64() - t_kernel0));  // role lifetimes
   }
   tc_fence_before();
   __syncthreads();
@@ -454,13 +527,22 @@ int vmma_check_watchdog(int device) {
   return AA_OK;
 }
 
+// The 16 profile counters of `device` (AA_VMMA_PROF=1): cycles summed over waiting warps, see aa_debug_counters.
+int vmma_read_counters(int device, unsigned long long* out, int reset) {
+  for (int i = 0; i < 16; i++) out[i] = 0;
+  if (device < 0 || device >= 64 || !g_dbg[device]) return AA_OK;
+  AA_CUDA_TRY(cudaMemcpy(out, reinterpret_cast<char*>(g_dbg[device]) + 32, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) AA_CUDA_TRY(cudaMemset(reinterpret_cast<char*>(g_dbg[device]) + 32, 0, 16 * sizeof(unsigned long long)));
+  return AA_OK;
+}
+
 static int vmma_prepare_device(int device) {
   std::lock_guard<std::mutex> lock(g_vplan_mu);
   if (device < 0 || device >= 64) return fail(AA_ERR_INVALID, "bad device ordinal");
   if (!g_dbg[device]) {
     int* d = nullptr;
-    AA_CUDA_TRY(cudaMalloc(&d, 4 * sizeof(int)));
-    AA_CUDA_TRY(cudaMemset(d, 0, 4 * sizeof(int)));
+    AA_CUDA_TRY(cudaMalloc(&d, 64 * sizeof(int)));
+    AA_CUDA_TRY(cudaMemset(d, 0, 64 * sizeof(int)));
     g_dbg[device] = d;
   }
   return AA_OK;
@@ -510,7 +592,8 @@ int launch_vmma(const void* in, const Layout& lin, void* out, const Layout& lout
   if (!have) {
     const int32_t* xs = tw->h_xmin.data();
     const int32_t* xz = tw->h_xsize.data();
-    const size_t fixed = (size_t)2 * P.b_bytes + sizeof(float) * VCOLS * VPITCH + BAR_BYTES + 1024 /*alignment slack*/;
+    const size_t fixed = (size_t)2 * P.b_bytes + sizeof(float) * VALLOC * VPITCH + BAR_BYTES + 1024 /*alignment slack*/;
+    const size_t stage_bytes = (size_t)P.b_bytes;  // one stage = one tile's K span
     const size_t cap_total = 227 * 1024;
     int n_strips = 1, strip_ox = (int)oW, kp = 0, wtab = 0;
     size_t tab_bytes = 0;
@@ -521,7 +604,16 @@ int launch_vmma(const void* in, const Layout& lin, void* out, const Layout& lout
       int shift = 0;
       for (int64_t a = 0; ok && a < oW; a += strip_ox) {
         const int64_t b = std::min<int64_t>(oW, a + strip_ox) - 1;
-        if (((int64_t)xs[b] + xz[b]) * Ci - (((int64_t)xs[a] * Ci) & ~15ll) > VCOLS) ok = false;
+        const int64_t f0 = ((int64_t)xs[a] * Ci) & ~15ll;
+        if (((int64_t)xs[b] + xz[b]) * Ci - f0 > VCOLS) ok = false;
+        // every pair may walk the strip's longest union window: keep first tap + longest * Ci inside the VALLOC columns
+        int64_t longest = 1;
+        for (int64_t o = a; o <= b; o += 2) {
+          const int64_t e1 = o + 1 <= b ? (int64_t)xs[o + 1] + xz[o + 1] : 0;
+          longest = std::max<int64_t>(longest, std::max<int64_t>((int64_t)xs[o] + xz[o], e1) - xs[o]);
+        }
+        for (int64_t o = a; ok && o <= b; o += 2)
+          if (((int64_t)xs[o] + longest) * Ci + (Ci - 1) - f0 > VALLOC) ok = false;
         for (int64_t o = a; o + 1 <= b; o += 2) shift = std::max<int>(shift, xs[o + 1] - xs[o]);
       }
       if (ok) {
@@ -529,16 +621,16 @@ int launch_vmma(const void* in, const Layout& lin, void* out, const Layout& lout
         const int np = (strip_ox + 1) / 2;
         wtab = (int)((size_t)np * kp * sizeof(float2));
         tab_bytes = (size_t)wtab + 16 + (size_t)np * Ci * sizeof(int4);
-        if (kp >= (1 << 16) || fixed + tab_bytes + 8 * STAGE_BYTES > cap_total) ok = false;
+        if (kp >= (1 << 16) || fixed + tab_bytes + 2 * stage_bytes > cap_total) ok = false;
       }
       if (ok) break;
     }
     n_strips = (int)((oW + strip_ox - 1) / strip_ox);
-    int nstage = (int)((cap_total - fixed - tab_bytes) / STAGE_BYTES);
+    int nstage = (int)((cap_total - fixed - tab_bytes) / stage_bytes);
     if (nstage > MAX_STAGES) nstage = MAX_STAGES;
-    if (nstage < 8) return fail(AA_ERR_UNSUPPORTED, "vmma: shared memory plan too large");
+    if (nstage < 2) return fail(AA_ERR_UNSUPPORTED, "vmma: shared memory plan too large");
     pl.n_strips = n_strips; pl.strip_ox = strip_ox; pl.kp = kp; pl.wtab_bytes = wtab; pl.nstage = nstage;
-    pl.smem = fixed + tab_bytes + (size_t)nstage * STAGE_BYTES;
+    pl.smem = fixed + tab_bytes + (size_t)nstage * stage_bytes;
     AA_CUDA_TRY(cudaDeviceGetAttribute(&pl.sms, cudaDevAttrMultiProcessorCount, th->device));
     if (gen) AA_CUDA_TRY(cudaFuncSetAttribute(aa_vmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap_total));
     else AA_CUDA_TRY(cudaFuncSetAttribute(aa_vmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap_total));
@@ -563,6 +655,12 @@ int launch_vmma(const void* in, const Layout& lin, void* out, const Layout& lout
   debug_env("AA_VMMA_SBO", sbo, &sbo);
   debug_env("AA_VMMA_LAYOUT", lay, &lay);
   P.desc_tmpl = ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)lay << 61);
+  // measured on cfg3 (strip of 32 pairs): 4 rows/thread 1.148 ms, 2 rows 1.185 ms, 8 rows 1.554 ms (one busy warp per
+  // group: latency-bound); narrow strips take 2 rows so that all four warps of a group have work
+  debug_env("AA_VMMA_R", ((pl.strip_ox + 1) / 2) * Ci > 16 ? 4 : 2, &v);
+  P.hr = (int)v;
+  debug_env("AA_VMMA_PROF", 0, &v);
+  P.prof = (int)v;
   debug_env("AA_VMMA_TIMEOUT_MS", 2000, &v);
   P.timeout_clk = v * 2000000ll;  // ~2 GHz
 
@@ -573,7 +671,7 @@ int launch_vmma(const void* in, const Layout& lin, void* out, const Layout& lout
   const cuuint64_t any16 = (cuuint64_t)lin.stride_h * (cuuint64_t)H;  // placeholder stride of a size-1 dimension
   const cuuint64_t strides[3] = {(cuuint64_t)lin.stride_h, lin.Cp > 1 ? (cuuint64_t)lin.stride_p : any16,
                                  n_img > 1 ? (cuuint64_t)lin.stride_n : any16};
-  const cuuint32_t box[4] = {TILE_M, KSTEP, 1, 1};
+  const cuuint32_t box[4] = {TILE_M, (cuuint32_t)(P.ksteps * KSTEP), 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(in), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

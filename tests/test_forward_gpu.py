@@ -153,6 +153,25 @@ def test_named_config_slices(cuda):
     assert np.abs(a - b).max() <= 1, e
 
 
+def test_cfg3_eight_images_all_paths(cuda):
+    """cfg3 at full per-image size on 8 images (24 planes): the tensor-core path (AUTO for uint8), the FP32-pipe streaming
+    kernel and the bit-exact general path against the oracle, plane by plane (a work split that mixed planes up would
+    show here, a single image would not)."""
+    from interpolate_antialiasing_b200 import capi
+    g = torch.Generator().manual_seed(3)
+    xu = torch.randint(0, 256, (8, 3, 2160, 3840), generator=g, dtype=torch.uint8)
+    xc = xu.to(cuda)
+    ya = _run(capi, xc, (512, 512), "cubic", False, capi.FLAG_AUTO)
+    ys = _run(capi, xc, (512, 512), "cubic", False, capi.FLAG_FORCE_STREAM)
+    yg = _run(capi, xc, (512, 512), "cubic", False, capi.FLAG_FORCE_GENERAL)
+    capi.check_device(0)
+    for n in range(8):
+        want = O.forward(xu[n:n + 1].float().numpy(), (512, 512), "cubic", False)
+        _close(ya[n:n + 1].cpu().numpy(), want)
+        _close(ys[n:n + 1].cpu().numpy(), want)
+        assert np.array_equal(yg[n:n + 1].cpu().numpy(), want), n
+
+
 def test_full_size_properties(cuda):
     """Size-independent properties at BASELINE sizes (a 16-image slab of cfg2; cfg3 full per-image size):
     constants are preserved (weights sum to 1), the op is linear, batch elements are independent,
@@ -269,7 +288,7 @@ def test_cuda_graph_capture_and_replay(cuda):
     graph.replay()
     torch.cuda.synchronize()
     _close(out.cpu().numpy(), O.forward(x.cpu().numpy(), (196, 320), "linear", False))
-    np.testing.assert_allclose(gin.cpu().numpy(), O.backward_adjoint(go.cpu().numpy(), x.shape, "linear", False), rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(gin.cpu().numpy(), O.backward_adjoint(go.cpu().numpy(), x.shape, "linear", False), rtol=1e-5, atol=4e-6)
 
 
 def test_fused_uint8_output(cuda, photo):

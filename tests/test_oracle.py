@@ -140,3 +140,34 @@ def test_forward_backward_bit_exact_vs_reference(ref_ext):
             for align in (False, True):
                 r = ref_ext.linear_backward(go, osz, list(shp), align)
                 assert np.array_equal(r.numpy(), O.backward_nonaa(go.numpy(), shp, align))
+
+
+def test_scale_factors_knob_matches_torch_aa():
+    """The oracle's `scale_factors` path (aa_interpolation_impl.h:735,740-742 -> compute_scales_value) against torch's
+    own CPU anti-aliased interpolate called with scale_factor / recompute_scale_factor=False: same tables up to torch's
+    different accumulation (tolerance as SURVEY Appendix C: a few 1e-4 on the 0..255 scale)."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand((1, 2, 57, 83), generator=g) * 255
+    for mode, tmode in (("linear", "bilinear"), ("cubic", "bicubic")):
+        for sf in ((0.37, 0.37), (0.5, 0.81), (1.7, 0.4)):
+            want = F.interpolate(x, scale_factor=sf, mode=tmode, antialias=True, recompute_scale_factor=False).numpy()
+            osize = want.shape[-2:]
+            got = O.forward(x.numpy(), osize, mode, False, scale_factors=sf)
+            assert np.abs(got - want).max() < 5e-4, (mode, sf, np.abs(got - want).max())
+            # and it differs from the in/out tables when floor(in*s)/in != s
+            plain = O.forward(x.numpy(), osize, mode, False)
+            if abs(osize[0] / 57 - sf[0]) > 1e-3 or abs(osize[1] / 83 - sf[1]) > 1e-3:
+                assert np.abs(got - plain).max() > 1e-3
+
+
+def test_reference_uint8_box_filter_is_unreachable(ref_ext):
+    """The reference's code intends `nearest_forward` (box filter) to accept uint8 and return uint8
+    (aa_interpolation_impl.h:566-570, :615-619), but compute_indices_weights overwrites interp_size (:210) before the
+    `interp_size > 1` dispatch (:608), so the call raises for Byte.  Pinned so that the product's uint8 -> uint8 box
+    filter is understood as an extension, not a parity claim."""
+    import torch
+    x = torch.randint(0, 256, (1, 2, 12, 16), dtype=torch.uint8)
+    with pytest.raises(RuntimeError, match="not implemented for 'Byte'"):
+        ref_ext.nearest_forward(x, (6, 8), False)

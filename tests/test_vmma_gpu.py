@@ -28,8 +28,8 @@ def _check(capi, x, osize, mode, align=False, flags=None):
 def test_vmma_shapes(cuda, mode, cl):
     from interpolate_antialiasing_b200 import capi
     g = torch.Generator().manual_seed(5)
-    cases = [((2, 3, 540, 960), (128, 128)), ((1, 1, 256, 512), (64, 512)), ((1, 4, 333, 208), (40, 300)),
-             ((3, 3, 200, 48), (33, 7)), ((1, 3, 1031, 400), (129, 90)), ((2, 1, 96, 4000), (31, 333))]
+    cases = [((2, 3, 540, 960), (128, 128)), ((1, 1, 256, 512), (64, 512)), ((1, 4, 333, 208), (56, 300)),
+             ((3, 3, 200, 48), (33, 7)), ((1, 3, 1031, 400), (160, 90)), ((2, 1, 96, 4000), (31, 333))]
     for shape, osize in cases:
         x = torch.randint(0, 256, shape, dtype=torch.uint8, generator=g).to(cuda)
         if cl:
@@ -45,11 +45,11 @@ def test_vmma_extreme_pixels(cuda):
     from interpolate_antialiasing_b200 import capi
     for fill in (255, 0):
         x = torch.full((1, 3, 700, 256), fill, dtype=torch.uint8, device=cuda)
-        _check(capi, x, (70, 50), "cubic")
+        _check(capi, x, (140, 50), "cubic")
         _check(capi, x, (100, 64), "linear")
     yy, xx = torch.meshgrid(torch.arange(700), torch.arange(256), indexing="ij")
     x = (((yy + xx) % 2) * 255).to(torch.uint8)[None, None].to(cuda)
-    _check(capi, x, (70, 50), "cubic")
+    _check(capi, x, (140, 50), "cubic")
 
 
 def test_vmma_is_auto_for_u8_downsampling_and_matches_stream(cuda):
