@@ -89,12 +89,62 @@ bool vmma_auto(const AxisTables* th, const AxisTables* tw) {
   if (mode == 0) return false;
   if (mode == 1) return true;
   (void)tw;
-  return th->scale_f >= 2.0f && th->xsize_max >= 5;
+  // measured on the uint8 sweep (gpurun_out/u8_probe3.txt -> DESIGN.md section 6): the tensor-core kernel beats the
+  // streaming, band and tile kernels at every vertical scale from 1x down to the 7x its K span allows
+  return th->scale_f >= 1.0f;
 }
 
 __global__ void widen_i32_i64(const int32_t* __restrict__ a, int64_t* __restrict__ b, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) b[i] = a[i];
+}
+
+// One launch: few taps on both axes (near scale 1 / upsampling) -> output-bound tile / band kernels; uint8 pixels with
+// vertical downsampling -> tensor-core vertical pass; otherwise (downsampling) -> input-bound streaming kernel.
+// AA_ERR_UNSUPPORTED when none of them takes the shape.
+int fused_dispatch(const void* in, int in_dtype, const Layout& lin, void* out, const Layout& lout, AxisTables* th, AxisTables* tw,
+                   int64_t H, int64_t W, int64_t oH, int64_t oW, uint32_t flags, const OutEpi& epi, cudaStream_t stream) {
+  int rc;
+  const bool want_vmma = in_dtype == AA_U8 && !(flags & (AA_FLAG_FORCE_STREAM | AA_FLAG_STREAM_TMA | AA_FLAG_STREAM_LDG)) &&
+                         ((flags & AA_FLAG_VMMA) || vmma_auto(th, tw));
+  if (want_vmma) {
+    rc = launch_vmma(in, lin, out, lout, th, tw, H, W, oH, oW, epi, stream);
+    if (rc != AA_ERR_UNSUPPORTED || (flags & AA_FLAG_VMMA)) return rc;
+  }
+  const bool few_taps = th->xsize_max <= 7 && tw->xsize_max <= 7;
+  if (few_taps && !(flags & AA_FLAG_FORCE_STREAM)) {
+    // mild vertical downsampling (1x..1.6x fewer rows): the band-walking variant; otherwise one tile per CTA
+    if (oH <= H && H * 5 <= oH * 8) {
+      rc = launch_band(in, in_dtype, lin, out, lout, fwd_axis(th), fwd_axis(tw), th->xsize_max, tw->xsize_max, epi, stream);
+      if (rc != AA_ERR_UNSUPPORTED) return rc;
+    }
+    rc = launch_tile(in, in_dtype, lin, out, lout, fwd_axis(th), fwd_axis(tw), th->xsize_max, tw->xsize_max, epi, stream);
+    if (rc != AA_ERR_UNSUPPORTED) return rc;
+  }
+  return launch_stream(in, in_dtype, lin, out, lout, th, tw, H, W, oH, oW, flags, epi, stream);
+}
+
+int two_pass(const aa_tensor_desc* in, const aa_tensor_desc* out, const Layout& lin, const Layout& lout, AxisTables* th, AxisTables* tw,
+             int filter, int align, uint32_t flags, const OutEpi& epi, cudaStream_t stream) {
+  if (epi.planar) return fail(AA_ERR_UNSUPPORTED, "two-pass: planar epilogue not supported");
+  int rc;
+  std::shared_ptr<AxisTables> ih, iw;  // identities: H -> H and oW -> oW
+  if ((rc = get_axis_tables(in->device, in->h, in->h, filter, align, AA_F32, 0.0, stream, &ih)) != AA_OK) return rc;
+  if ((rc = get_axis_tables(in->device, out->w, out->w, filter, align, AA_F32, 0.0, stream, &iw)) != AA_OK) return rc;
+  // intermediate [n, c, H, oW] float32 in the input's memory format, dense
+  Layout lt = lin;
+  const int64_t row = out->w * lin.Ci;
+  lt.stride_h = row;
+  if (lin.Cp > 1) { lt.stride_p = in->h * row; lt.stride_n = lt.stride_p * lin.Cp; }
+  else { lt.stride_p = 0; lt.stride_n = in->h * row; }
+  const size_t bytes = sizeof(float) * (size_t)in->n * in->c * in->h * out->w;
+  void* tmp = nullptr;
+  AA_CUDA_TRY(cudaMallocAsync(&tmp, bytes, stream));
+  rc = fused_dispatch(in->data, in->dtype, lin, tmp, lt, ih.get(), tw, in->h, in->w, in->h, out->w, flags & ~AA_FLAG_VMMA, OutEpi(), stream);
+  if (rc == AA_OK) rc = fused_dispatch(tmp, AA_F32, lt, out->data, lout, th, iw.get(), in->h, out->w, out->h, out->w, flags & ~AA_FLAG_VMMA, epi, stream);
+  const cudaError_t e = cudaFreeAsync(tmp, stream);
+  if (rc == AA_OK && e != cudaSuccess) return cuda_fail(e, "cudaFreeAsync");
+  return rc;
 }
 
 int forward_impl(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align, uint32_t flags,
@@ -150,30 +200,13 @@ int forward_impl(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter
   if ((rc = get_axis_tables(in->device, in->h, out->h, filter, align, tdtype, sc ? sc->scale_h : 0.0, stream, &th)) != AA_OK) return rc;
   if ((rc = get_axis_tables(in->device, in->w, out->w, filter, align, tdtype, sc ? sc->scale_w : 0.0, stream, &tw)) != AA_OK) return rc;
   if (!(flags & AA_FLAG_FORCE_GENERAL) && tdtype == AA_F32) {
-    // few taps on both axes (near scale 1 / upsampling): output-bound -> tile kernel;
-    // otherwise (downsampling): input-bound -> streaming kernel.
-    const bool few_taps = th->xsize_max <= 7 && tw->xsize_max <= 7;
-    if (few_taps && !(flags & (AA_FLAG_FORCE_STREAM | AA_FLAG_VMMA))) {
-      // mild vertical downsampling (1x..1.6x fewer rows): the band-walking variant; otherwise one tile per CTA
-      if (out->h <= in->h && in->h * 5 <= out->h * 8) {
-        rc = launch_band(in->data, in->dtype, lin, out->data, lout, fwd_axis(th.get()), fwd_axis(tw.get()), th->xsize_max,
-                         tw->xsize_max, epi, stream);
-        if (rc != AA_ERR_UNSUPPORTED) return rc;
-      }
-      rc = launch_tile(in->data, in->dtype, lin, out->data, lout, fwd_axis(th.get()), fwd_axis(tw.get()), th->xsize_max,
-                       tw->xsize_max, epi, stream);
-      if (rc != AA_ERR_UNSUPPORTED) return rc;
-    }
-    // uint8 pixels, many vertical taps: vertical pass on the tensor cores (aa_vmma.cu)
-    if (in->dtype == AA_U8 && !(flags & (AA_FLAG_FORCE_STREAM | AA_FLAG_STREAM_TMA | AA_FLAG_STREAM_LDG)) &&
-        ((flags & AA_FLAG_VMMA) || vmma_auto(th.get(), tw.get()))) {
-      rc = launch_vmma(in->data, lin, out->data, lout, th.get(), tw.get(), in->h, in->w, out->h, out->w, epi, stream);
-      if (rc != AA_ERR_UNSUPPORTED || (flags & AA_FLAG_VMMA)) return rc;
-    }
-    rc = launch_stream(in->data, in->dtype, lin, out->data, lout, th.get(), tw.get(), in->h, in->w, out->h, out->w,
-                       flags, epi, stream);
-    if (rc == AA_OK) return rc;
-    if (rc != AA_ERR_UNSUPPORTED || (flags & AA_FLAG_FORCE_STREAM)) return rc;
+    rc = fused_dispatch(in->data, in->dtype, lin, out->data, lout, th.get(), tw.get(), in->h, in->w, out->h, out->w, flags, epi, stream);
+    if (rc != AA_ERR_UNSUPPORTED || (flags & (AA_FLAG_FORCE_STREAM | AA_FLAG_VMMA))) return rc;
+    // No fused kernel takes this shape (typically: upsampling in H, many-tap downsampling in W).  Two launches with
+    // an intermediate, the reference's own structure (W pass into a temp, then H pass: aa_interpolation_impl.h:655-679),
+    // each through a fused kernel with the identity on the other axis (weights {1, 0}: exact).
+    rc = two_pass(in, out, lin, lout, th.get(), tw.get(), filter, align, flags, epi, stream);
+    if (rc != AA_ERR_UNSUPPORTED) return rc;
   } else if (flags & AA_FLAG_FORCE_STREAM) {
     return fail(AA_ERR_UNSUPPORTED, "stream path: f32/u8 only");
   }

@@ -75,6 +75,7 @@ struct VParams {
   long long timeout_clk;
   int prof;
   int hr;  // rows per thread in the horizontal pass (2, 4 or 8)
+  int vt;  // V chunk rotation shift (31 = none), see vchunk()
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -203,13 +204,20 @@ __device__ __forceinline__ void item_next(const VParams& P, Item& it) {
 // loads of the chunks coalesce and the V loads spread over all banks (pitch 36).  Window bookkeeping
 // (Wp, pinfo) is the pair form of aa_stream_common.cuh::strip_setup; as there, a lane never reads a column outside
 // its own pair's windows (the pointer stops advancing, the weights past the window are zero padding).
-template <bool GEN, int R, int CI>
+// Position of 4-row chunk `cq` inside column x of V.  With vt < 31 the chunk is rotated by (x >> vt): pair columns that
+// are a multiple of 8 flat columns apart (integer scales 2, 4, 8: the padded pitch alone maps them to the same banks,
+// a 16-way conflict on the 128-bit loads) then land in different bank groups; 2^vt = the largest power of two dividing
+// the pair spacing, chosen by the host plan.  vt = 31: no rotation (odd spacings are conflict-free by the pitch).
+__device__ __forceinline__ int vchunk(int cq, int x, int vt) { return (cq + (x >> vt)) & 7; }
+
+template <bool GEN, int R, int CI, bool ROT>
 __device__ __forceinline__ void hphase_T(const VParams& P, const float* __restrict__ V, const float2* __restrict__ Wp,
                                          const int4* __restrict__ pinfo, int64_t op_off, int npc, int tg, int grp, int oy0, int nrows) {
   constexpr int NCH = GROWS / R;       // row chunks of the group's 8 rows
   constexpr int PPW = 32 / NCH;        // pair-columns per warp iteration
   constexpr int SH = R == 8 ? 5 : (R == 4 ? 4 : 3);   // log2(PPW)
   const int Ci = CI ? CI : P.S.Ci;
+  const int vt = P.vt;
   const int64_t osh = P.S.lout.stride_h;
   for (int it = tg; ((it >> 5) << SH) < npc; it += NTC / NGRP) {
     const int pc = ((it >> 5) << SH) | (it & (PPW - 1));
@@ -229,17 +237,25 @@ __device__ __forceinline__ void hphase_T(const VParams& P, const float* __restri
 #pragma unroll 4
     for (int j = 0; j < lenm; j++) {
       const float2 w2 = wr[j];
+      const float* vj;
+      if constexpr (ROT) {
+        const int x = pi.x + j * Ci;
+        vj = V + x * VPITCH + 4 * vchunk(r0 >> 2, x, vt) + (r0 & 3);
+      } else {
+        vj = vp + j * vstep;
+      }
       if constexpr (R >= 4) {
 #pragma unroll
         for (int q = 0; q < R; q += 4) {
-          const float4 v = *reinterpret_cast<const float4*>(vp + j * vstep + q);
+          const float4 v = ROT && q ? *reinterpret_cast<const float4*>(V + (pi.x + j * Ci) * VPITCH + 4 * vchunk((r0 >> 2) + 1, pi.x + j * Ci, vt))
+                                   : *reinterpret_cast<const float4*>(vj + q);
           h[q + 0] = __ffma2_rn(make_float2(v.x, v.x), w2, h[q + 0]);
           h[q + 1] = __ffma2_rn(make_float2(v.y, v.y), w2, h[q + 1]);
           h[q + 2] = __ffma2_rn(make_float2(v.z, v.z), w2, h[q + 2]);
           h[q + 3] = __ffma2_rn(make_float2(v.w, v.w), w2, h[q + 3]);
         }
       } else {
-        const float2 v = *reinterpret_cast<const float2*>(vp + j * vstep);
+        const float2 v = *reinterpret_cast<const float2*>(vj);
         h[0] = __ffma2_rn(make_float2(v.x, v.x), w2, h[0]);
         h[1] = __ffma2_rn(make_float2(v.y, v.y), w2, h[1]);
       }
@@ -261,11 +277,15 @@ __device__ __forceinline__ void hphase_T(const VParams& P, const float* __restri
 template <bool GEN, int R>
 __device__ __forceinline__ void hphase_ci(const VParams& P, const float* V, const float2* Wp, const int4* pinfo, int64_t op_off,
                                           int npc, int tg, int grp, int oy0, int nrows) {
+  if (P.vt < 31) {  // rotated chunks: per-tap address arithmetic instead of immediates
+    hphase_T<GEN, R, 0, true>(P, V, Wp, pinfo, op_off, npc, tg, grp, oy0, nrows);
+    return;
+  }
   switch (P.S.Ci) {  // compile-time interleave: the tap offsets become immediates
-    case 1: hphase_T<GEN, R, 1>(P, V, Wp, pinfo, op_off, npc, tg, grp, oy0, nrows); break;
-    case 3: hphase_T<GEN, R, 3>(P, V, Wp, pinfo, op_off, npc, tg, grp, oy0, nrows); break;
-    case 4: hphase_T<GEN, R, 4>(P, V, Wp, pinfo, op_off, npc, tg, grp, oy0, nrows); break;
-    default: hphase_T<GEN, R, 0>(P, V, Wp, pinfo, op_off, npc, tg, grp, oy0, nrows); break;
+    case 1: hphase_T<GEN, R, 1, false>(P, V, Wp, pinfo, op_off, npc, tg, grp, oy0, nrows); break;
+    case 3: hphase_T<GEN, R, 3, false>(P, V, Wp, pinfo, op_off, npc, tg, grp, oy0, nrows); break;
+    case 4: hphase_T<GEN, R, 4, false>(P, V, Wp, pinfo, op_off, npc, tg, grp, oy0, nrows); break;
+    default: hphase_T<GEN, R, 0, false>(P, V, Wp, pinfo, op_off, npc, tg, grp, oy0, nrows); break;
   }
 }
 
@@ -408,7 +428,8 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty0 + 8 * acc);  // accumulators are in registers: the MMA warp may reuse the buffer
-          float* vrow = V + (size_t)(s * TILE_M + q * 32 + lane) * VPITCH + half * GROWS;
+          const int vx = s * TILE_M + q * 32 + lane;
+          float* vcol = V + (size_t)vx * VPITCH;
           const float2 c0v = make_float2(c0, c0), c1v = make_float2(c1, c1), c2v = make_float2(c2, c2), k0v = make_float2(k0, k0);
 #pragma unroll
           for (int e = 0; e < GROWS; e += 4) {
@@ -427,7 +448,7 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
               o[p] = u.x;
               o[p + 1] = u.y;
             }
-            *reinterpret_cast<float4*>(vrow + e) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(vcol + 4 * vchunk((half * GROWS + e) >> 2, vx, P.vt)) = make_float4(o[0], o[1], o[2], o[3]);
           }
           if (P.prof) wacc[11] += clock64() - t_e0;  // whole epilogue of the tile (TMEM read + convert + store)
         }
@@ -440,8 +461,7 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
       const int nrows = min(OYB, (int)P.S.oH - it.oyb * OYB);
       // rows per thread: the pass is bound by shared-memory bandwidth (2 B of V per FMA for a column pair + 4/R B of
       // weights), so more rows per thread is less traffic; fewer rows only when the strip is too narrow to occupy the warps
-      if (P.hr == 8) hphase_ci<GEN, 8>(P, V, Wp, pinfo, op, strip_npc, tc & (NTC / NGRP - 1), half, it.oyb * OYB, nrows);
-      else if (P.hr == 4) hphase_ci<GEN, 4>(P, V, Wp, pinfo, op, strip_npc, tc & (NTC / NGRP - 1), half, it.oyb * OYB, nrows);
+      if (P.hr == 4) hphase_ci<GEN, 4>(P, V, Wp, pinfo, op, strip_npc, tc & (NTC / NGRP - 1), half, it.oyb * OYB, nrows);
       else hphase_ci<GEN, 2>(P, V, Wp, pinfo, op, strip_npc, tc & (NTC / NGRP - 1), half, it.oyb * OYB, nrows);
       const long long t_h2 = clock64();
       group_sync(half);  // V rows of this group may be overwritten
@@ -493,7 +513,7 @@ struct VPlanKey {
   }
 };
 struct VPlan {
-  int n_strips, strip_ox, kp, wtab_bytes, nstage, sms;
+  int n_strips, strip_ox, kp, wtab_bytes, nstage, sms, vt;
   size_t smem;
 };
 std::mutex g_vplan_mu;
@@ -630,6 +650,17 @@ int launch_vmma(const void* in, const Layout& lin, void* out, const Layout& lout
     if (nstage > MAX_STAGES) nstage = MAX_STAGES;
     if (nstage < 2) return fail(AA_ERR_UNSUPPORTED, "vmma: shared memory plan too large");
     pl.n_strips = n_strips; pl.strip_ox = strip_ox; pl.kp = kp; pl.wtab_bytes = wtab; pl.nstage = nstage;
+    {
+      // spacing of adjacent pair columns in flat elements (taken in the middle of the row): even -> rotate the chunks
+      const int64_t om = std::min<int64_t>(oW - 1, (oW / 2) & ~1ll);
+      const int64_t d = om + 2 < oW ? ((int64_t)xs[om + 2] - xs[om]) * Ci : 1;
+      int tz = 31;
+      if (d > 0 && (d & 1) == 0) {
+        tz = 0;
+        while (tz < 5 && ((d >> tz) & 1) == 0) tz++;
+      }
+      pl.vt = tz;
+    }
     pl.smem = fixed + tab_bytes + (size_t)nstage * stage_bytes;
     AA_CUDA_TRY(cudaDeviceGetAttribute(&pl.sms, cudaDevAttrMultiProcessorCount, th->device));
     if (gen) AA_CUDA_TRY(cudaFuncSetAttribute(aa_vmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap_total));
@@ -641,6 +672,7 @@ int launch_vmma(const void* in, const Layout& lin, void* out, const Layout& lout
   }
   P.S.n_strips = pl.n_strips; P.S.strip_ox = pl.strip_ox; P.S.kp = pl.kp; P.S.wtab_bytes = pl.wtab_bytes;
   P.nstage = pl.nstage;
+  P.vt = pl.vt;
   P.total_items = lin.planes * pl.n_strips * P.n_oyb;
   P.dbg = g_dbg[th->device];
 
