@@ -82,7 +82,7 @@ struct AxisTables {
   // [ksteps*32 input rows][128] int8 matrix (3 balanced base-256 digits per weight, 128-byte-swizzled rows)
   int8_t* vq = nullptr;       // [vq_noyb][vq_ksteps*32][128]
   float* vq_meta = nullptr;   // {c0, c1, c2, K0, (int) s}
-  int vq_ksteps = 0, vq_noyb = 0;
+  int vq_ksteps = 0, vq_noyb = 0, vq_oyb = 0;  // K steps per block, number of blocks, output rows per block (32 or 16)
   // host mirrors of the integer tables (for launch planning)
   std::vector<int32_t> h_xmin, h_xsize, h_omin, h_osize;
   ~AxisTables();
@@ -101,7 +101,7 @@ int ensure_slot_tables(AxisTables* t, int A, cudaStream_t stream);
 int ensure_slot_tables_adj(AxisTables* t, int A, cudaStream_t stream);
 // Quantised weight matrices of the tensor-core vertical pass; AA_ERR_UNSUPPORTED when a block of `oyb` output rows
 // spans more than max_ksteps*kstep input rows.
-int ensure_vq_tables(AxisTables* t, int oyb, int kstep, int max_ksteps, cudaStream_t stream);
+int ensure_vq_tables(AxisTables* t, int oyb_max, int kstep, int max_ksteps, cudaStream_t stream);
 int clear_table_cache();
 // Host-only K computation (no device), same arithmetic as the table kernel.
 int host_interp_size(int64_t in, int64_t out, int filter, int align, int dtype, double user_scale = 0.0);

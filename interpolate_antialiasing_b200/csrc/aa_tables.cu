@@ -307,7 +307,7 @@ __global__ void aa_tables_vq_scale(const float* __restrict__ w, int64_t n, float
 }
 // One thread per (output row, tap): three int8 digits into the row block's matrix.  Element (k, n) of a block lives at
 // byte k*128 + (((n >> 4) ^ (k & 7)) << 4) + (n & 15): the 128-byte swizzle the MMA's shared-memory descriptor
-// expects, applied here so that a plain bulk copy can land the matrix.  n = digit*oyb + (row inside the block).
+// expects, applied here so that a plain bulk copy can land the matrix.  n = digit*32 + (row inside the block).
 __global__ void aa_tables_vq(int64_t out, int K, int oyb, int krows, const int32_t* __restrict__ xmin,
                              const int32_t* __restrict__ xsize, const float* __restrict__ w, const float* __restrict__ meta,
                              int8_t* __restrict__ bq) {
@@ -329,7 +329,7 @@ __global__ void aa_tables_vq(int64_t out, int K, int oyb, int krows, const int32
   int8_t* row = bq + ((size_t)b * krows + k) * 128;
   const int dig[3] = {d0, d1, d2};
   for (int l = 0; l < 3; l++) {
-    const int n = l * oyb + i;
+    const int n = l * 32 + i;  // 32 accumulator columns per digit whatever the block height (16 or 32 rows)
     row[(((n >> 4) ^ (k & 7)) << 4) + (n & 15)] = (int8_t)dig[l];
   }
 }
@@ -584,22 +584,27 @@ int ensure_slot_tables_adj(AxisTables* t, int A, cudaStream_t stream) {
   return AA_OK;
 }
 
-int ensure_vq_tables(AxisTables* t, int oyb, int kstep, int max_ksteps, cudaStream_t stream) {
+int ensure_vq_tables(AxisTables* t, int oyb_max, int kstep, int max_ksteps, cudaStream_t stream) {
   std::lock_guard<std::mutex> lock(t->mu);
   if (t->dtype != AA_F32) return fail(AA_ERR_UNSUPPORTED, "vq tables are float only");
   if (t->vq) return AA_OK;  // complete: the builder synchronised before publishing
   if (t->vq_ksteps < 0) return fail(AA_ERR_UNSUPPORTED, "vmma: a block of output rows spans too many input rows");
   const int64_t out = t->out;
-  const int noyb = (int)((out + oyb - 1) / oyb);
-  int span = 1;
-  for (int b = 0; b < noyb; b++) {
-    const int64_t o0 = (int64_t)b * oyb, o1 = std::min<int64_t>(out, o0 + oyb) - 1;
-    span = std::max<int>(span, t->h_xmin[o1] + t->h_xsize[o1] - t->h_xmin[o0]);
-  }
-  const int ksteps = (span + kstep - 1) / kstep;
-  if (ksteps > max_ksteps) {
-    t->vq_ksteps = -1;
-    return fail(AA_ERR_UNSUPPORTED, "vmma: a block of output rows spans too many input rows");
+  // block height: 32 output rows, or 16 when 32 rows would span more than max_ksteps*kstep input rows (scales > ~7x)
+  int oyb = oyb_max, noyb = 0, ksteps = 0;
+  for (;; oyb /= 2) {
+    noyb = (int)((out + oyb - 1) / oyb);
+    int span = 1;
+    for (int b = 0; b < noyb; b++) {
+      const int64_t o0 = (int64_t)b * oyb, o1 = std::min<int64_t>(out, o0 + oyb) - 1;
+      span = std::max<int>(span, t->h_xmin[o1] + t->h_xsize[o1] - t->h_xmin[o0]);
+    }
+    ksteps = (span + kstep - 1) / kstep;
+    if (ksteps <= max_ksteps) break;
+    if (oyb <= 16) {
+      t->vq_ksteps = -1;
+      return fail(AA_ERR_UNSUPPORTED, "vmma: a block of output rows spans too many input rows");
+    }
   }
   const int krows = ksteps * kstep;
   const size_t bytes = (size_t)noyb * krows * 128;
@@ -625,6 +630,7 @@ int ensure_vq_tables(AxisTables* t, int oyb, int kstep, int max_ksteps, cudaStre
   t->vq_meta = meta;
   t->vq_ksteps = ksteps;
   t->vq_noyb = noyb;
+  t->vq_oyb = oyb;
   t->vq = vq;
   return AA_OK;
 }

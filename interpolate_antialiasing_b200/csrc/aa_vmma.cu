@@ -68,6 +68,7 @@ struct VParams {
   const int8_t* bq;     // [n_oyb][ksteps*32][128] weight limbs, 128B-swizzled rows (aa_tables.cu)
   const float* qmeta;   // {c0, c1, c2, K0}: fp32 = fma(m2, c2, fma(m1, c1, fma(m0, c0, K0)))
   int ksteps, n_oyb, nstage, b_bytes, Cp_in;
+  int oyb;  // output rows per item: OYB (32), or 16 for vertical scales whose 32-row blocks would not fit the K span
   int64_t total_items;
   uint32_t idesc;       // tcgen05 instruction descriptor
   uint64_t desc_tmpl;   // shared-memory matrix descriptor without the start address
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
         mbar_expect_tx(bfull0 + 8 * bslot, (uint32_t)P.b_bytes);
         bulk_g2s(sB + (uint32_t)bslot * P.b_bytes, P.bq + (size_t)it.oyb * P.b_bytes, (uint32_t)P.b_bytes, bfull0 + 8 * bslot);
         if (++bslot == 2) { bslot = 0; bphase ^= 1; }
-        const int y0 = __ldg(P.S.xmin_h + it.oyb * OYB);
+        const int y0 = __ldg(P.S.xmin_h + it.oyb * P.oyb);
         const int pc = (int)(it.plane % P.Cp_in), pn = (int)(it.plane / P.Cp_in);
         for (int s = 0; s < it.ntiles; s++) {  // one TMA box per tile: 128 flat columns x ksteps*32 rows
           ok = mbar_wait(W, empty0 + 8 * stage, phase ^ 1, 2);
@@ -416,7 +417,11 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
         if (ok) ok = mbar_wait(W, tfull0 + 8 * acc, aphase, 6);
         ok = __all_sync(0xffffffffu, ok);  // the TMEM loads below are warp-collective
         tc_fence_after();
-        if (ok) {
+        if (ok && half * GROWS >= P.oyb) {  // 16-row items: the upper two groups have no rows; they only release the buffer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        } else if (ok) {
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + half * GROWS);
           int l0[GROWS], l1[GROWS], l2[GROWS];
           const long long t_e0 = P.prof ? clock64() : 0;
@@ -458,11 +463,12 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
       group_sync(half);  // this group's 16 rows of all tiles are in V
       const long long t_h1 = clock64();
       const int64_t op = (it.plane / P.S.lout.Cp) * P.S.lout.stride_n + (it.plane % P.S.lout.Cp) * P.S.lout.stride_p;
-      const int nrows = min(OYB, (int)P.S.oH - it.oyb * OYB);
+      const int nrows = min(P.oyb, (int)P.S.oH - it.oyb * P.oyb);
       // rows per thread: the pass is bound by shared-memory bandwidth (2 B of V per FMA for a column pair + 4/R B of
       // weights), so more rows per thread is less traffic; fewer rows only when the strip is too narrow to occupy the warps
-      if (P.hr == 4) hphase_ci<GEN, 4>(P, V, Wp, pinfo, op, strip_npc, tc & (NTC / NGRP - 1), half, it.oyb * OYB, nrows);
-      else hphase_ci<GEN, 2>(P, V, Wp, pinfo, op, strip_npc, tc & (NTC / NGRP - 1), half, it.oyb * OYB, nrows);
+      if (half * GROWS >= nrows) {}  // no row of this group in the item (last block of the image, or 16-row items)
+      else if (P.hr == 4) hphase_ci<GEN, 4>(P, V, Wp, pinfo, op, strip_npc, tc & (NTC / NGRP - 1), half, it.oyb * P.oyb, nrows);
+      else hphase_ci<GEN, 2>(P, V, Wp, pinfo, op, strip_npc, tc & (NTC / NGRP - 1), half, it.oyb * P.oyb, nrows);
       const long long t_h2 = clock64();
       group_sync(half);  // V rows of this group may be overwritten
       if (P.prof) {
@@ -596,7 +602,7 @@ int launch_vmma(const void* in, const Layout& lin, void* out, const Layout& lout
   P.S.xmin_h = th->xmin; P.S.xsize_h = th->xsize;
   P.S.xmin_w = tw->xmin; P.S.xsize_w = tw->xsize; P.S.w_w = (const float*)tw->w; P.S.Kw = tw->K;
   P.S.aln = 16; P.S.pairs = 1; P.S.pad = 0;
-  P.bq = th->vq; P.qmeta = th->vq_meta; P.ksteps = th->vq_ksteps; P.n_oyb = th->vq_noyb;
+  P.bq = th->vq; P.qmeta = th->vq_meta; P.ksteps = th->vq_ksteps; P.n_oyb = th->vq_noyb; P.oyb = th->vq_oyb;
   P.b_bytes = P.ksteps * STAGE_BYTES;
   P.Cp_in = lin.Cp;
 

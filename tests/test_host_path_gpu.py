@@ -92,3 +92,69 @@ def test_concurrent_callers_on_their_own_streams(cuda):
     for t in ts:
         t.join()
     assert not errs, errs
+
+
+def test_host_entry_validates_before_touching_buffers(cuda):
+    """dtype / strides are checked up front; a bad description never reaches the memcpy."""
+    from interpolate_antialiasing_b200 import capi
+    L = capi.lib()
+    x = torch.rand((2, 3, 16, 16))
+    o = torch.empty((2, 3, 8, 8))
+    di, do = capi.desc(x, 0), capi.desc(o, 0)
+    di.dtype = capi.F16  # would make the copy read past the buffer if it were sized from it
+    assert L.aa_resize_forward_host(ctypes.byref(di), ctypes.byref(do), 1, 0, 0) == -1
+    di = capi.desc(x, 0)
+    di.stride_h = 32  # padded rows inside an image
+    assert L.aa_resize_forward_host(ctypes.byref(di), ctypes.byref(do), 1, 0, 0) == -2
+    di = capi.desc(x[:1], 0)
+    di.stride_c = 999  # n == 1 used to skip every stride check
+    assert L.aa_resize_forward_host(ctypes.byref(di), ctypes.byref(capi.desc(o[:1], 0)), 1, 0, 0) == -2
+    assert L.aa_resize_forward_host(ctypes.byref(capi.desc(x, 0)), ctypes.byref(do), 7, 0, 0) == -1  # bad filter
+    # mismatched memory formats
+    xcl = x.contiguous(memory_format=torch.channels_last)
+    assert L.aa_resize_forward_host(ctypes.byref(capi.desc(xcl, 0)), ctypes.byref(do), 1, 0, 0) == -2
+
+
+def test_host_multi_device_runner(cuda):
+    """aa_resize_forward_host_multi: one process, the batch sharded by image over the devices it is given; bit-identical
+    to the single-device entry (SURVEY 8(e)).  With one GPU the device list [0] still exercises the sharded code path;
+    with >= 2 GPUs the default list (all devices) is used as well."""
+    from interpolate_antialiasing_b200 import capi
+    g = torch.Generator().manual_seed(8)
+    x = (torch.rand((9, 3, 150, 260), generator=g) * 255).pin_memory()
+    for mode, osize in (("linear", (40, 70)), ("cubic", (33, 51))):
+        want = torch.empty((9, 3) + osize).pin_memory()
+        capi.resize_forward_host(x, want, mode, False, device=0)
+        got = torch.empty((9, 3) + osize).pin_memory()
+        capi.resize_forward_host_multi(x, got, mode, False, devices=[0])
+        assert torch.equal(got, want)
+        if torch.cuda.device_count() >= 2:
+            got2 = torch.zeros((9, 3) + osize).pin_memory()
+            capi.resize_forward_host_multi(x, got2, mode, False, devices=None)
+            assert torch.equal(got2, want)
+            got3 = torch.zeros((9, 3) + osize).pin_memory()
+            capi.resize_forward_host_multi(x, got3, mode, False, devices=[1, 0])
+            assert torch.equal(got3, want)
+    with pytest.raises(capi.AAError):
+        capi.resize_forward_host_multi(x, got, "linear", False, devices=[0, 0])
+
+
+def test_table_cache_is_bounded_lru(cuda):
+    """Variable-size pipelines (random-resized-crop) must not grow the cache without bound: more distinct
+    sizes than AA_TABLE_CACHE_MAX (256 entries) go through, results stay right, and re-used early sizes still work."""
+    from interpolate_antialiasing_b200 import capi
+    capi.lib().aa_clear_table_cache()
+    g = torch.Generator().manual_seed(13)
+    x = (torch.rand((1, 1, 64, 700), generator=g) * 255).to(cuda)
+    first = None
+    for k in range(300):  # 300 distinct W tables + 1 H table > 256
+        xs = x[:, :, :, : 380 + k].contiguous()
+        y = capi.resize_forward(xs, (32, 100), "linear")
+        if k == 0:
+            first = y.clone()
+    torch.cuda.synchronize()
+    y0 = capi.resize_forward(x[:, :, :, :380].contiguous(), (32, 100), "linear")  # evicted by now: rebuilt
+    torch.cuda.synchronize()
+    assert torch.equal(y0, first)
+    want = O.forward(x[:, :, :, :380].cpu().numpy(), (32, 100), "linear", False)
+    _close(y0.cpu().numpy(), want)

@@ -40,6 +40,23 @@ def test_vmma_shapes(cuda, mode, cl):
             _check(capi, x, osize, mode, align)
 
 
+def test_vmma_large_scales_use_16_row_items(cuda):
+    """Vertical scales above ~7x: a block of 32 output rows would span more than the 256 input rows one MMA tile holds,
+    so the items shrink to 16 output rows (same kernel, upper two epilogue groups idle)."""
+    from interpolate_antialiasing_b200 import capi
+    g = torch.Generator().manual_seed(21)
+    for shape, osize, mode in [((1, 3, 700, 256), (70, 50), "cubic"), ((2, 1, 1024, 1024), (128, 128), "cubic"),
+                               ((1, 3, 1024, 512), (100, 77), "linear"), ((1, 4, 1200, 320), (83, 100), "nearest")]:
+        x = torch.randint(0, 256, shape, dtype=torch.uint8, generator=g).to(cuda)
+        _check(capi, x, osize, mode)
+        _check(capi, x.contiguous(memory_format=torch.channels_last), osize, mode)
+    # beyond what even 16-row items can hold: refused (AUTO falls back to the streaming kernel)
+    x = torch.randint(0, 256, (1, 1, 2048, 256), dtype=torch.uint8, generator=g).to(cuda)
+    with pytest.raises(capi.AAError):
+        capi.resize_forward(x, (64, 64), "cubic", False, capi.FLAG_VMMA)
+    _check(capi, x, (64, 64), "cubic", flags=capi.FLAG_AUTO)
+
+
 def test_vmma_extreme_pixels(cuda):
     """All-255 / all-0 / checkerboard inputs: the int32 limb sums are at their largest magnitude."""
     from interpolate_antialiasing_b200 import capi
