@@ -63,6 +63,14 @@ typedef enum aa_dtype {
 #define AA_FLAG_VMMA 64u         /* uint8 input: vertical pass on the tensor cores (tcgen05 kind::i8 + TMA, aa_vmma.cu);
                                     fails with AA_ERR_UNSUPPORTED if not eligible.  AUTO picks it for uint8 inputs
                                     downsampled >= 2x vertically                                      */
+#define AA_FLAG_STRICT_NONFINITE 128u /* propagate NaN/Inf exactly like the reference: an output is non-finite iff a tap with
+                                    index j < xsize of one of its two windows is (aa_interpolation_impl.h:73-85 never
+                                    touches j >= xsize).  The fast kernels multiply a few zero-weight neighbours past a
+                                    window (unrolled tap loops, accumulator slots not yet open), so with AUTO one NaN/Inf
+                                    pixel can also reach outputs whose window ends within K-1 taps before it; finite
+                                    inputs -- every image -- are unaffected.  This flag routes float inputs to the gather
+                                    kernel that touches in-window taps only (same arithmetic as AA_FLAG_FORCE_GENERAL);
+                                    uint8 inputs are always finite and keep their fast path.                      */
 #define AA_FLAG_ROUND_NEAREST 32u /* uint8 output: round to nearest (PIL) instead of truncating (.byte()) */
 
 /* A 4-D tensor view [n, c, h, w] with ELEMENT strides, resident on CUDA device `device`.
@@ -179,6 +187,23 @@ int aa_resize_forward_sf(const aa_tensor_desc* in, const aa_tensor_desc* out, in
                          const aa_scales* scales, uint32_t flags, void* cuda_stream);
 int aa_resize_backward_sf(const aa_tensor_desc* grad_out, const aa_tensor_desc* grad_in, int filter, int align_corners,
                           const aa_scales* scales, uint32_t flags, void* cuda_stream);
+
+/* Variable-size inputs -> one fixed-size batch (the decode-adjacent caller: N decoded images of different sizes, one
+ * (oH, oW) training resolution; the reference takes one [N,C,H,W] tensor per call, test.py:52-58, so such a caller would
+ * loop).  Image i ([c, h_i, w_i], dtype and pixel layout common to all) is resized into out[i].  Images are grouped by
+ * size class (h, w, strides); inside a class, runs of images that sit at a constant pointer distance and go to consecutive
+ * output slots (slices of one staging buffer, the usual case for a decoder writing into a pool) take ONE launch per run;
+ * isolated images take one launch each.  Every launch after the first of a class is a table-cache and plan-cache hit
+ * (no allocation, no synchronisation).  aa_epilogue may be NULL (plain float32 / uint8 output as aa_resize_forward). */
+typedef struct aa_image_desc {
+  void* data;        /* device pointer to image i */
+  int64_t h, w;      /* its size */
+  int64_t stride_h;  /* elements between rows */
+  int64_t stride_c;  /* elements between channel planes (channels_first); ignored for channels_last (stride_c == 1) */
+} aa_image_desc;
+int aa_resize_forward_ragged(const aa_image_desc* images, int32_t count, int32_t dtype, int64_t channels, int32_t channels_last,
+                             const aa_tensor_desc* out, int filter, int align_corners, uint32_t flags,
+                             const aa_epilogue* epilogue, void* cuda_stream, int32_t* launches_out);
 
 /* grad_in = Wh^T * grad_out * Ww : the true adjoint of aa_resize_forward, gather form, no atomics,
  * no zero-fill pass.  Replaces ti_upsample_bilinear2d_backward_cpu,

@@ -13,11 +13,12 @@ BOX, TRIANGLE, CUBIC = 0, 1, 2
 U8, F32, F64, F16, BF16 = 0, 1, 2, 3, 4
 FLAG_AUTO, FLAG_FORCE_GENERAL, FLAG_FORCE_STREAM, FLAG_STREAM_TMA, FLAG_STREAM_LDG, FLAG_ROUND_NEAREST = 0, 1, 2, 4, 8, 32
 FLAG_VMMA = 64
+FLAG_STRICT_NONFINITE = 128
 FILTERS = {"nearest": BOX, "box": BOX, "bilinear": TRIANGLE, "linear": TRIANGLE, "bicubic": CUBIC, "cubic": CUBIC}
 
 EXPORTS = [
     "aa_abi_version", "aa_last_error", "aa_interp_size", "aa_host_tables", "aa_build_tables", "aa_build_tables_sf", "aa_warm_tables",
-    "aa_clear_table_cache", "aa_check_device", "aa_debug_counters", "aa_resize_forward", "aa_resize_forward_sf", "aa_resize_backward_sf", "aa_resize_forward_ex", "aa_resize_backward",
+    "aa_clear_table_cache", "aa_check_device", "aa_debug_counters", "aa_resize_forward", "aa_resize_forward_sf", "aa_resize_backward_sf", "aa_resize_forward_ex", "aa_resize_forward_ragged", "aa_resize_backward",
     "aa_resize_backward_nonaa_bilinear", "aa_resize_forward_host", "aa_resize_forward_host_multi", "aa_launch_count",
 ]
 
@@ -36,6 +37,11 @@ class TablesDesc(ctypes.Structure):
 
 class Epilogue(ctypes.Structure):
     _fields_ = [("normalize", ctypes.c_int32), ("scale", ctypes.c_float * 4), ("bias", ctypes.c_float * 4)]
+
+
+class ImageDesc(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("h", ctypes.c_int64), ("w", ctypes.c_int64), ("stride_h", ctypes.c_int64),
+                ("stride_c", ctypes.c_int64)]
 
 
 class Scales(ctypes.Structure):
@@ -70,6 +76,7 @@ def lib():
         L.aa_resize_forward_sf.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, P(Scales), u32, vp]
         L.aa_resize_backward_sf.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, P(Scales), u32, vp]
         L.aa_resize_forward_ex.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, u32, P(Epilogue), vp]
+        L.aa_resize_forward_ragged.argtypes = [P(ImageDesc), i32, i32, i64, i32, P(TensorDesc), i32, i32, u32, P(Epilogue), vp, P(i32)]
         L.aa_resize_backward.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, u32, vp]
         L.aa_resize_backward_nonaa_bilinear.argtypes = [P(TensorDesc), P(TensorDesc), i32, vp]
         L.aa_resize_forward_host.argtypes = [P(TensorDesc), P(TensorDesc), i32, i32, u32]
@@ -182,6 +189,40 @@ def resize_forward_ex(x, output_size, filter, out, scale=None, bias=None, align_
     check(lib().aa_resize_forward_ex(ctypes.byref(di), ctypes.byref(do), _filter(filter), int(align_corners), flags,
                                      ctypes.byref(e), _stream(x)))
     return out
+
+
+def resize_forward_ragged(images, output_size, filter, out=None, align_corners=False, flags=FLAG_AUTO, scale=None, bias=None):
+    """Variable-size images -> one fixed-size batch (aa_resize_forward_ragged).  `images`: list of CUDA tensors, all [C,H_i,W_i]
+    (planar) or all [H_i,W_i,C] (HWC, as a decoder emits), same dtype.  Returns (out [N,C,oH,oW], launches)."""
+    import torch
+    hwc = images[0].dim() == 3 and images[0].stride(-1) == 1 and images[0].shape[-1] <= 4 and images[0].stride(1) == images[0].shape[-1]
+    C = images[0].shape[-1] if hwc else images[0].shape[0]
+    oH, oW = int(output_size[0]), int(output_size[1])
+    if out is None:
+        out = torch.empty((len(images), C, oH, oW), dtype=torch.float32, device=images[0].device,
+                          memory_format=torch.channels_last if hwc else torch.contiguous_format)
+    arr = (ImageDesc * len(images))()
+    for i, t in enumerate(images):
+        if hwc:
+            arr[i] = ImageDesc(t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), 1)
+        else:
+            arr[i] = ImageDesc(t.data_ptr(), t.shape[1], t.shape[2], t.stride(1), t.stride(0))
+    e = None
+    if scale is not None:
+        e = Epilogue()
+        e.normalize = 1
+        for i in range(4):
+            e.scale[i] = float(scale[i]) if i < len(scale) else 1.0
+            e.bias[i] = float(bias[i]) if bias is not None and i < len(bias) else 0.0
+    elif out.dtype in (torch.float16, torch.bfloat16) or (hwc and out.is_contiguous() and C > 1):
+        e = Epilogue()
+        e.normalize = 0
+    n = ctypes.c_int32(0)
+    do = desc(out)
+    check(lib().aa_resize_forward_ragged(arr, len(images), _dtype_code(images[0]), C, int(hwc), ctypes.byref(do), _filter(filter),
+                                         int(align_corners), flags, ctypes.byref(e) if e is not None else None, _stream(out),
+                                         ctypes.byref(n)))
+    return out, n.value
 
 
 def resize_backward(grad_out, input_size, filter, align_corners=False, nonaa=False, flags=FLAG_AUTO, scales=None, out=None):

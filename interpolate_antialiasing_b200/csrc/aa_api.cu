@@ -1,6 +1,9 @@
 // aa_api.cu -- the C ABI (include/aa_resize.h): validation, table cache lookups, path selection.
 // No torch types, no exceptions across the boundary, no CPU fallback.
+#include <algorithm>
 #include <cstdlib>
+#include <tuple>
+#include <vector>
 #include <string.h>
 
 #include <mutex>
@@ -32,11 +35,13 @@ int classify_layout(const aa_tensor_desc& t, bool prefer_channels_last, Layout* 
                                        "(stride_c == 1, stride_w == c); make it contiguous in one of the two formats");
   Layout r;
   if (use_cl) {
-    r.planes = t.n; r.Cp = 1; r.Ci = (int)t.c; r.stride_n = t.stride_n; r.stride_p = 0;
+    // the stride of a size-1 batch dimension carries no information (torch reports arbitrary values there): 0 keeps
+    // the alignment tests of the vectorised / TMA paths from tripping over it
+    r.planes = t.n; r.Cp = 1; r.Ci = (int)t.c; r.stride_n = t.n == 1 ? 0 : t.stride_n; r.stride_p = 0;
     r.stride_h = (t.h == 1) ? t.w * t.c : t.stride_h;
     if (r.stride_h < t.w * t.c) return fail(AA_ERR_UNSUPPORTED, "channels_last rows overlap (stride_h < w*c)");
   } else {
-    r.planes = t.n * t.c; r.Cp = (int)t.c; r.Ci = 1; r.stride_n = t.stride_n; r.stride_p = (t.c == 1) ? 0 : t.stride_c;
+    r.planes = t.n * t.c; r.Cp = (int)t.c; r.Ci = 1; r.stride_n = t.n == 1 ? 0 : t.stride_n; r.stride_p = (t.c == 1) ? 0 : t.stride_c;
     r.stride_h = (t.h == 1) ? t.w : t.stride_h;
     if (r.stride_h < t.w) return fail(AA_ERR_UNSUPPORTED, "channels_first rows overlap (stride_h < w)");
   }
@@ -199,6 +204,7 @@ int forward_impl(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter
   std::shared_ptr<AxisTables> th, tw;
   if ((rc = get_axis_tables(in->device, in->h, out->h, filter, align, tdtype, sc ? sc->scale_h : 0.0, stream, &th)) != AA_OK) return rc;
   if ((rc = get_axis_tables(in->device, in->w, out->w, filter, align, tdtype, sc ? sc->scale_w : 0.0, stream, &tw)) != AA_OK) return rc;
+  if ((flags & AA_FLAG_STRICT_NONFINITE) && in->dtype != AA_U8) flags |= AA_FLAG_FORCE_GENERAL;
   if (!(flags & AA_FLAG_FORCE_GENERAL) && tdtype == AA_F32) {
     rc = fused_dispatch(in->data, in->dtype, lin, out->data, lout, th.get(), tw.get(), in->h, in->w, out->h, out->w, flags, epi, stream);
     if (rc != AA_ERR_UNSUPPORTED || (flags & (AA_FLAG_FORCE_STREAM | AA_FLAG_VMMA))) return rc;
@@ -357,6 +363,64 @@ int aa_resize_forward_ex(const aa_tensor_desc* in, const aa_tensor_desc* out, in
 int aa_resize_forward_sf(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align_corners,
                          const aa_scales* scales, uint32_t flags, void* cuda_stream) {
   return forward_impl(in, out, filter, align_corners, flags, (cudaStream_t)cuda_stream, nullptr, scales);
+}
+
+int aa_resize_forward_ragged(const aa_image_desc* images, int32_t count, int32_t dtype, int64_t channels, int32_t channels_last,
+                             const aa_tensor_desc* out, int filter, int align_corners, uint32_t flags, const aa_epilogue* epilogue,
+                             void* cuda_stream, int32_t* launches_out) {
+  int rc;
+  if (launches_out) *launches_out = 0;
+  if (count < 0 || (count > 0 && !images)) return fail(AA_ERR_INVALID, "aa_resize_forward_ragged: bad image list");
+  if ((rc = check_desc(out, "output")) != AA_OK) return rc;
+  if ((rc = check_filter(filter)) != AA_OK) return rc;
+  if (out->n != count || out->c != channels) return fail(AA_ERR_INVALID, "output must be [count, channels, oH, oW]");
+  if (dtype != AA_U8 && dtype != AA_F32 && dtype != AA_F64) return fail(AA_ERR_INVALID, "input dtype must be u8, f32 or f64");
+  const int64_t es = dtype == AA_U8 ? 1 : (dtype == AA_F32 ? 4 : 8);
+  for (int i = 0; i < count; i++) {
+    if (!images[i].data || images[i].h <= 0 || images[i].w <= 0)
+      return fail(AA_ERR_INVALID, "aa_resize_forward_ragged: image " + std::to_string(i) + " is empty");
+    if (images[i].stride_h < images[i].w * (channels_last ? channels : 1))
+      return fail(AA_ERR_INVALID, "aa_resize_forward_ragged: rows of image " + std::to_string(i) + " overlap");
+  }
+  // order: size class, then address
+  std::vector<int> idx((size_t)count);
+  for (int i = 0; i < count; i++) idx[(size_t)i] = i;
+  auto cls = [&](int i) { const aa_image_desc& m = images[i]; return std::make_tuple(m.h, m.w, m.stride_h, channels_last ? (int64_t)1 : m.stride_c); };
+  std::sort(idx.begin(), idx.end(), [&](int a, int b) {
+    if (cls(a) != cls(b)) return cls(a) < cls(b);
+    return a < b;
+  });
+  int launches = 0;
+  for (size_t p = 0; p < idx.size();) {
+    const int i0 = idx[p];
+    // extend the run: same class, consecutive output slots, constant pointer distance
+    size_t q = p + 1;
+    int64_t delta = 0;
+    while (q < idx.size() && cls(idx[q]) == cls(i0) && idx[q] == idx[q - 1] + 1) {
+      const int64_t d = (const char*)images[idx[q]].data - (const char*)images[idx[q - 1]].data;
+      if (d <= 0 || d % es) break;
+      if (q == p + 1) delta = d;
+      else if (d != delta) break;
+      q++;
+    }
+    const aa_image_desc& m = images[i0];
+    aa_tensor_desc di;
+    di.data = m.data; di.dtype = dtype; di.device = out->device;
+    di.n = (int64_t)(q - p); di.c = channels; di.h = m.h; di.w = m.w;
+    di.stride_n = q - p > 1 ? delta / es : m.h * m.stride_h * (channels_last ? 1 : channels);
+    di.stride_h = m.stride_h;
+    if (channels_last) { di.stride_c = 1; di.stride_w = channels; }
+    else { di.stride_c = m.stride_c; di.stride_w = 1; }
+    aa_tensor_desc dd = *out;
+    dd.n = di.n;
+    dd.data = (char*)out->data + (size_t)i0 * out->stride_n * (out->dtype == AA_U8 ? 1 : (out->dtype == AA_F64 ? 8 : (out->dtype == AA_F32 ? 4 : 2)));
+    rc = forward_impl(&di, &dd, filter, align_corners, flags, (cudaStream_t)cuda_stream, epilogue);
+    if (rc != AA_OK) return rc;
+    launches++;
+    p = q;
+  }
+  if (launches_out) *launches_out = launches;
+  return AA_OK;
 }
 
 static int backward_impl(const aa_tensor_desc* gout, const aa_tensor_desc* gin, int filter, int align_corners, uint32_t flags,

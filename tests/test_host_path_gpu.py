@@ -158,3 +158,33 @@ def test_table_cache_is_bounded_lru(cuda):
     assert torch.equal(y0, first)
     want = O.forward(x[:, :, :, :380].cpu().numpy(), (32, 100), "linear", False)
     _close(y0.cpu().numpy(), want)
+
+
+def test_ragged_images_to_fixed_batch(cuda):
+    """aa_resize_forward_ragged: decoded images of different sizes -> one [N,C,oH,oW] batch.  Images carved out of one
+    pool at a constant distance and bound for consecutive slots share a launch; results equal per-image calls bit for bit
+    and the oracle within tolerance."""
+    from interpolate_antialiasing_b200 import capi
+    g = torch.Generator().manual_seed(23)
+    sizes = [(120, 160), (120, 160), (120, 160), (90, 200), (64, 64), (120, 160), (90, 200)]
+    # images 0..2 are consecutive slices of one pool (one launch); the others are separate allocations
+    pool = torch.randint(0, 256, (3, 120, 160, 3), dtype=torch.uint8, generator=g).to(cuda)
+    imgs = [pool[0], pool[1], pool[2]] + [torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, generator=g).to(cuda) for h, w in sizes[3:]]
+    out, launches = capi.resize_forward_ragged(imgs, (48, 56), "linear")
+    torch.cuda.synchronize()
+    assert launches == 5 and out.shape == (7, 3, 48, 56) and out.is_contiguous(memory_format=torch.channels_last)
+    for i, im in enumerate(imgs):
+        x = im.permute(2, 0, 1)[None]  # channels_last NCHW view of the HWC image
+        single = capi.resize_forward(x, (48, 56), "linear")
+        assert torch.equal(out[i:i + 1], single), i
+        want = O.forward(x.float().cpu().numpy(), (48, 56), "linear", False)
+        _close(out[i:i + 1].cpu().numpy(), want)
+    # planar float images, normalising epilogue into fp16
+    fimgs = [(torch.rand((3, h, w), generator=g) * 255).to(cuda) for h, w in [(70, 90), (33, 47), (70, 90)]]
+    o16 = torch.empty((3, 3, 32, 40), dtype=torch.float16, device=cuda)
+    o16, launches = capi.resize_forward_ragged(fimgs, (32, 40), "cubic", out=o16, scale=[1 / 58.0] * 3, bias=[-2.0] * 3)
+    torch.cuda.synchronize()
+    assert launches == 3
+    for i, im in enumerate(fimgs):
+        want = O.forward(im[None].cpu().numpy(), (32, 40), "cubic", False) / 58.0 - 2.0
+        assert np.abs(o16[i:i + 1].float().cpu().numpy() - want).max() < 4e-3
