@@ -349,6 +349,7 @@ template <int KH, typename in_t>
 int launch_kh(BParams& P, int kw, int64_t nb, const BandedAxis& ah, int nc, cudaStream_t s, GeomPlan& G) {
   if (kw <= 2) return launch_gen<KH, 2, in_t>(P, nb, ah, nc, s, G);
   if (kw <= 3) return launch_gen<KH, 3, in_t>(P, nb, ah, nc, s, G);
+  if (kw <= 4) return launch_gen<KH, 4, in_t>(P, nb, ah, nc, s, G);
   if (kw <= 5) return launch_gen<KH, 5, in_t>(P, nb, ah, nc, s, G);
   if (kw <= 7) return launch_gen<KH, 7, in_t>(P, nb, ah, nc, s, G);
   return fail(AA_ERR_UNSUPPORTED, "band: more than 7 horizontal taps");
@@ -358,6 +359,7 @@ template <typename in_t>
 int launch_in(BParams& P, int kh, int kw, int64_t nb, const BandedAxis& ah, int nc, cudaStream_t s, GeomPlan& G) {
   if (kh <= 2) return launch_kh<2, in_t>(P, kw, nb, ah, nc, s, G);
   if (kh <= 3) return launch_kh<3, in_t>(P, kw, nb, ah, nc, s, G);
+  if (kh <= 4) return launch_kh<4, in_t>(P, kw, nb, ah, nc, s, G);
   if (kh <= 5) return launch_kh<5, in_t>(P, kw, nb, ah, nc, s, G);
   if (kh <= 7) return launch_kh<7, in_t>(P, kw, nb, ah, nc, s, G);
   return fail(AA_ERR_UNSUPPORTED, "band: more than 7 vertical taps");

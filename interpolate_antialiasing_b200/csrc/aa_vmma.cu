@@ -275,22 +275,12 @@ __device__ __forceinline__ void hphase_T(const VParams& P, const float* __restri
     }
   }
 }
-template <bool GEN, int R>
-__device__ __forceinline__ void hphase_ci(const VParams& P, const float* V, const float2* Wp, const int4* pinfo, int64_t op_off,
-                                          int npc, int tg, int grp, int oy0, int nrows) {
-  if (P.vt < 31) {  // rotated chunks: per-tap address arithmetic instead of immediates
-    hphase_T<GEN, R, 0, true>(P, V, Wp, pinfo, op_off, npc, tg, grp, oy0, nrows);
-    return;
-  }
-  switch (P.S.Ci) {  // compile-time interleave: the tap offsets become immediates
-    case 1: hphase_T<GEN, R, 1, false>(P, V, Wp, pinfo, op_off, npc, tg, grp, oy0, nrows); break;
-    case 3: hphase_T<GEN, R, 3, false>(P, V, Wp, pinfo, op_off, npc, tg, grp, oy0, nrows); break;
-    case 4: hphase_T<GEN, R, 4, false>(P, V, Wp, pinfo, op_off, npc, tg, grp, oy0, nrows); break;
-    default: hphase_T<GEN, R, 0, false>(P, V, Wp, pinfo, op_off, npc, tg, grp, oy0, nrows); break;
-  }
-}
-
-template <bool GEN>
+// GEN: decode-adjacent epilogue; CI: compile-time channel interleave of the flat rows (0 = runtime); HR: rows per thread in
+// the horizontal pass; ROT: rotated V chunks (even pair spacings); OYBR: output rows per item (32, or 16 for scales > ~7x).
+// One instantiation per combination keeps each kernel's code small: with four epilogue groups in different phases the
+// instruction caches hold both the epilogue and the horizontal pass (a kernel that carried every variant behind runtime
+// switches measured 7-11 % slower on cfg3).
+template <bool GEN, int CI, int HR, bool ROT, int OYBR>
 __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ CUtensorMap tmap, const VParams P) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -353,7 +343,7 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
         mbar_expect_tx(bfull0 + 8 * bslot, (uint32_t)P.b_bytes);
         bulk_g2s(sB + (uint32_t)bslot * P.b_bytes, P.bq + (size_t)it.oyb * P.b_bytes, (uint32_t)P.b_bytes, bfull0 + 8 * bslot);
         if (++bslot == 2) { bslot = 0; bphase ^= 1; }
-        const int y0 = __ldg(P.S.xmin_h + it.oyb * P.oyb);
+        const int y0 = __ldg(P.S.xmin_h + it.oyb * OYBR);
         const int pc = (int)(it.plane % P.Cp_in), pn = (int)(it.plane / P.Cp_in);
         for (int s = 0; s < it.ntiles; s++) {  // one TMA box per tile: 128 flat columns x ksteps*32 rows
           ok = mbar_wait(W, empty0 + 8 * stage, phase ^ 1, 2);
@@ -417,7 +407,7 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
         if (ok) ok = mbar_wait(W, tfull0 + 8 * acc, aphase, 6);
         ok = __all_sync(0xffffffffu, ok);  // the TMEM loads below are warp-collective
         tc_fence_after();
-        if (ok && half * GROWS >= P.oyb) {  // 16-row items: the upper two groups have no rows; they only release the buffer
+        if (ok && half * GROWS >= OYBR) {  // 16-row items: the upper two groups have no rows; they only release the buffer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
@@ -453,7 +443,8 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
               o[p] = u.x;
               o[p + 1] = u.y;
             }
-            *reinterpret_cast<float4*>(vcol + 4 * vchunk((half * GROWS + e) >> 2, vx, P.vt)) = make_float4(o[0], o[1], o[2], o[3]);
+            float* vdst = ROT ? vcol + 4 * vchunk((half * GROWS + e) >> 2, vx, P.vt) : vcol + half * GROWS + e;
+            *reinterpret_cast<float4*>(vdst) = make_float4(o[0], o[1], o[2], o[3]);
           }
           if (P.prof) wacc[11] += clock64() - t_e0;  // whole epilogue of the tile (TMEM read + convert + store)
         }
@@ -463,12 +454,11 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
       group_sync(half);  // this group's 16 rows of all tiles are in V
       const long long t_h1 = clock64();
       const int64_t op = (it.plane / P.S.lout.Cp) * P.S.lout.stride_n + (it.plane % P.S.lout.Cp) * P.S.lout.stride_p;
-      const int nrows = min(P.oyb, (int)P.S.oH - it.oyb * P.oyb);
+      const int nrows = min(OYBR, (int)P.S.oH - it.oyb * OYBR);
       // rows per thread: the pass is bound by shared-memory bandwidth (2 B of V per FMA for a column pair + 4/R B of
       // weights), so more rows per thread is less traffic; fewer rows only when the strip is too narrow to occupy the warps
-      if (half * GROWS >= nrows) {}  // no row of this group in the item (last block of the image, or 16-row items)
-      else if (P.hr == 4) hphase_ci<GEN, 4>(P, V, Wp, pinfo, op, strip_npc, tc & (NTC / NGRP - 1), half, it.oyb * P.oyb, nrows);
-      else hphase_ci<GEN, 2>(P, V, Wp, pinfo, op, strip_npc, tc & (NTC / NGRP - 1), half, it.oyb * P.oyb, nrows);
+      if (half * GROWS < nrows)  // else: no row of this group in the item (last block of the image, or 16-row items)
+        hphase_T<GEN, HR, CI, ROT>(P, V, Wp, pinfo, op, strip_npc, tc & (NTC / NGRP - 1), half, it.oyb * OYBR, nrows);
       const long long t_h2 = clock64();
       group_sync(half);  // V rows of this group may be overwritten
       if (P.prof) {
@@ -532,6 +522,30 @@ int debug_env(const char* name, long long dflt, long long* out) {
   return e != nullptr;
 }
 
+}  // namespace
+
+namespace {
+typedef void (*VKernel)(const CUtensorMap, const VParams);
+constexpr size_t cap_total_bytes = 227 * 1024;
+template <bool GEN, int CI, int HR, bool ROT>
+VKernel pick_oyb(int oyb) {
+  return oyb == 16 ? aa_vmma_kernel<GEN, CI, HR, ROT, 16> : aa_vmma_kernel<GEN, CI, HR, ROT, 32>;
+}
+template <bool GEN, int CI, bool ROT>
+VKernel pick_hr(int hr, int oyb) { return hr == 4 ? pick_oyb<GEN, CI, 4, ROT>(oyb) : pick_oyb<GEN, CI, 2, ROT>(oyb); }
+template <bool GEN>
+VKernel pick_ci(int ci, int hr, bool rot, int oyb) {
+  if (rot) return pick_hr<GEN, 0, true>(hr, oyb);  // rotated chunks: per-tap address arithmetic, runtime interleave
+  switch (ci) {
+    case 1: return pick_hr<GEN, 1, false>(hr, oyb);
+    case 3: return pick_hr<GEN, 3, false>(hr, oyb);
+    case 4: return pick_hr<GEN, 4, false>(hr, oyb);
+    default: return pick_hr<GEN, 0, false>(hr, oyb);
+  }
+}
+VKernel pick_kernel(bool gen, int ci, int hr, bool rot, int oyb) {
+  return gen ? pick_ci<true>(ci, hr, rot, oyb) : pick_ci<false>(ci, hr, rot, oyb);
+}
 }  // namespace
 
 void vmma_plan_clear() {
@@ -669,8 +683,6 @@ int launch_vmma(const void* in, const Layout& lin, void* out, const Layout& lout
     }
     pl.smem = fixed + tab_bytes + (size_t)nstage * stage_bytes;
     AA_CUDA_TRY(cudaDeviceGetAttribute(&pl.sms, cudaDevAttrMultiProcessorCount, th->device));
-    if (gen) AA_CUDA_TRY(cudaFuncSetAttribute(aa_vmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap_total));
-    else AA_CUDA_TRY(cudaFuncSetAttribute(aa_vmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap_total));
     if ((rc = vmma_prepare_device(th->device)) != AA_OK) return rc;
     std::lock_guard<std::mutex> lock(g_vplan_mu);
     if (g_vplans.size() > 4096) g_vplans.clear();
@@ -717,8 +729,10 @@ int launch_vmma(const void* in, const Layout& lin, void* out, const Layout& lout
   if (cr != CUDA_SUCCESS) return fail(AA_ERR_UNSUPPORTED, "vmma: cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")");
 
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(pl.sms, P.total_items));
-  if (gen) aa_vmma_kernel<true><<<(unsigned)grid, NT, pl.smem, stream>>>(tmap, P);
-  else aa_vmma_kernel<false><<<(unsigned)grid, NT, pl.smem, stream>>>(tmap, P);
+  const VKernel kern = pick_kernel(gen, P.vt < 31 ? 0 : Ci, P.hr, P.vt < 31, P.oyb);
+  if (!kern) return fail(AA_ERR_UNSUPPORTED, "vmma: no kernel instantiation for this shape");
+  AA_CUDA_TRY(ensure_smem_attr(kern, th->device, cap_total_bytes));
+  kern<<<(unsigned)grid, NT, pl.smem, stream>>>(tmap, P);
   AA_LAUNCH_CHECK("aa_vmma_kernel");
   return AA_OK;
 }
