@@ -61,6 +61,13 @@ constexpr int MAX_KSTEPS = 8;
 constexpr int NWC = 16, NTC = NWC * 32, NT = NTC + 64;  // 16 epilogue warps + producer + MMA issuer
 constexpr int NGRP = 4, GROWS = OYB / NGRP;             // 4 independent epilogue groups of 4 warps, 8 output rows each
 constexpr int BAR_BYTES = 1024;
+// Wait-time counters (aa_debug_counters, scripts/vmma_prof.py) are compiled in only with -DAA_VMMA_PROFILE: the
+// kernel is sensitive to its code size (see the note above aa_vmma_kernel).
+#ifdef AA_VMMA_PROFILE
+constexpr bool kProf = true;
+#else
+constexpr bool kProf = false;
+#endif
 constexpr int MAX_STAGES = 40;
 
 struct VParams {
@@ -107,7 +114,7 @@ __device__ __forceinline__ bool mbar_wait(const Watch& w, uint32_t bar, uint32_t
   const long long t0 = clock64();
   for (int spin = 0;; spin++) {
     if (mbar_try(bar, parity)) {
-      if (w.prof) w.acc[code] += clock64() - t0;
+      if (kProf && w.prof) w.acc[code] += clock64() - t0;
       return true;
     }
     if ((spin & 63) == 63) {
@@ -320,7 +327,7 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   long long wacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const Watch W{abort_flag, P.dbg, P.timeout_clk, P.prof, wacc};
-  const long long t_kernel0 = clock64();
+  const long long t_kernel0 = kProf ? clock64() : 0;
   if (warp >= 2) {
     // V: finite everywhere from the start (lanes may read zero-weight taps past their own window)
     for (int i = t - 64; i < VALLOC * VPITCH / 4; i += NTC) reinterpret_cast<float4*>(V)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -414,12 +421,12 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
         } else if (ok) {
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + half * GROWS);
           int l0[GROWS], l1[GROWS], l2[GROWS];
-          const long long t_e0 = P.prof ? clock64() : 0;
+          const long long t_e0 = kProf && P.prof ? clock64() : 0;
           tmem_ld8(taddr, l0);
           tmem_ld8(taddr + OYB, l1);
           tmem_ld8(taddr + 2 * OYB, l2);
           tmem_ld_wait();
-          if (P.prof) wacc[7] += clock64() - t_e0;  // TMEM read
+          if (kProf && P.prof) wacc[7] += clock64() - t_e0;  // TMEM read
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty0 + 8 * acc);  // accumulators are in registers: the MMA warp may reuse the buffer
@@ -446,29 +453,29 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
             float* vdst = ROT ? vcol + 4 * vchunk((half * GROWS + e) >> 2, vx, P.vt) : vcol + half * GROWS + e;
             *reinterpret_cast<float4*>(vdst) = make_float4(o[0], o[1], o[2], o[3]);
           }
-          if (P.prof) wacc[11] += clock64() - t_e0;  // whole epilogue of the tile (TMEM read + convert + store)
+          if (kProf && P.prof) wacc[11] += clock64() - t_e0;  // whole epilogue of the tile (TMEM read + convert + store)
         }
         if (++acc == NACC) { acc = 0; aphase ^= 1; }
       }
-      const long long t_h0 = clock64();
+      const long long t_h0 = kProf ? clock64() : 0;
       group_sync(half);  // this group's 16 rows of all tiles are in V
-      const long long t_h1 = clock64();
+      const long long t_h1 = kProf ? clock64() : 0;
       const int64_t op = (it.plane / P.S.lout.Cp) * P.S.lout.stride_n + (it.plane % P.S.lout.Cp) * P.S.lout.stride_p;
       const int nrows = min(OYBR, (int)P.S.oH - it.oyb * OYBR);
       // rows per thread: the pass is bound by shared-memory bandwidth (2 B of V per FMA for a column pair + 4/R B of
       // weights), so more rows per thread is less traffic; fewer rows only when the strip is too narrow to occupy the warps
       if (half * GROWS < nrows)  // else: no row of this group in the item (last block of the image, or 16-row items)
         hphase_T<GEN, HR, CI, ROT>(P, V, Wp, pinfo, op, strip_npc, tc & (NTC / NGRP - 1), half, it.oyb * OYBR, nrows);
-      const long long t_h2 = clock64();
+      const long long t_h2 = kProf ? clock64() : 0;
       group_sync(half);  // V rows of this group may be overwritten
-      if (P.prof) {
+      if (kProf && P.prof) {
         wacc[8] += t_h1 - t_h0;        // barrier before the horizontal pass
         wacc[9] += t_h2 - t_h1;        // horizontal pass
         wacc[10] += clock64() - t_h2;  // barrier after it
       }
     }
   }
-  if (P.prof && lane == 0) {
+  if (kProf && P.prof && lane == 0) {
     unsigned long long* pc = reinterpret_cast<unsigned long long*>(P.dbg) + 4;
     for (int k = 1; k < 12; k++)
       if (wacc[k]) atomicAdd(pc + k, (unsigned long long)wacc[k]);
