@@ -730,9 +730,11 @@ int launch_vmma(const void* in, const Layout& lin, void* out, const Layout& lout
                                  n_img > 1 ? (cuuint64_t)lin.stride_n : any16};
   const cuuint32_t box[4] = {TILE_M, (cuuint32_t)(P.ksteps * KSTEP), 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
+  debug_env("AA_VMMA_L2PROMO", 1, &v);  // 0 none, 1 64B, 2 128B, 3 256B
+  const CUtensorMapL2promotion promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                     : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(in), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(AA_ERR_UNSUPPORTED, "vmma: cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")");
 
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(pl.sms, P.total_items));
