@@ -262,7 +262,10 @@ int launch_cfg(SParams& P, const StreamTables& T, int device, cudaStream_t strea
   // at the tail (measured +1 % on cfg2 in two same-box A/B runs; 3x was not reproducible; each extra cut costs one window's halo rows)
   // but never cut work finer than about one column (oH output rows) per CTA
   static const int gmul = [] { const char* e = getenv("AA_STREAM_GRID_MUL"); return e ? std::max(1, atoi(e)) : 2; }();  // tuning knob
-  const int64_t want = std::min<int64_t>((int64_t)pl.max_grid * gmul, std::max<int64_t>(pl.max_grid, P.total_units / P.oH));
+  // ... and always whole waves: 1.5 waves (cfg2 at 128 images: 896 columns over 592 resident CTAs) left every other SM idle
+  // through the second half of the kernel, 0.69 instead of 0.88 of peak -- the shard size of 2-GPU strong scaling
+  const int64_t waves = std::max<int64_t>(1, std::min<int64_t>(gmul, (P.total_units / P.oH) / std::max(1, pl.max_grid)));
+  const int64_t want = (int64_t)pl.max_grid * waves;
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(want, P.total_units / min_units));
   if constexpr (PADDABLE) {
     if (P.pad) {
