@@ -17,6 +17,8 @@
 // Tap counts KH/KW are template parameters (loops fully unrolled); weights beyond a window's true
 // size are zero.  Summation: horizontal then vertical, FMA, ascending taps (the bit-exact non-FMA
 // order is aa_general.cu's job).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "aa_common.cuh"
@@ -299,7 +301,8 @@ int launch_k(BParams& P, int64_t planes, const BandedAxis& ah, int nc_max, cudaS
   constexpr int HR = (KH + 1 + 3) / 4;
   P.pcp = (nc_max + (KW - 1) * P.Ci + 3 + 3) & ~3;  // + up to 3 lead columns (aligned 16-byte copies); multiple of 4
   // chunk height: 16 output rows measured best at 0.75x..1x (bilinear and bicubic), 8 when 16 do not fit 4 CTAs/SM
-  const int tys[2] = {16, 8};
+  static const int ty_env = [] { const char* e = getenv("AA_BAND_TY"); return e ? atoi(e) : 0; }();  // tuning knob
+  const int tys[2] = {ty_env > 0 ? ty_env : 16, 8};
   const size_t limits[2] = {56 * 1024, 113 * 1024};
   int best_ty = G.ty, best_pr = G.nr;
   size_t best_smem = G.smem;
@@ -322,7 +325,8 @@ int launch_k(BParams& P, int64_t planes, const BandedAxis& ah, int nc_max, cudaS
   P.n_chunks = (P.out_h + P.ty - 1) / P.ty;
   if (planes <= 0 || P.n_chunks <= 0) return AA_OK;
   // segments: enough CTAs to fill the GPU many times over (tail effect), otherwise as long as possible
-  const int64_t target_ctas = 148 * 64;
+  static const int cta_env = [] { const char* e = getenv("AA_BAND_CTAS"); return e ? atoi(e) : 0; }();  // tuning knob
+  const int64_t target_ctas = 148 * (cta_env > 0 ? cta_env : 64);
   const int64_t bands = (int64_t)P.tiles_x * planes;
   int64_t nseg = std::min<int64_t>(P.n_chunks, std::max<int64_t>(1, (target_ctas + bands - 1) / bands));
   P.seg_chunks = (int)((P.n_chunks + nseg - 1) / nseg);
