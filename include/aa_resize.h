@@ -63,14 +63,18 @@ typedef enum aa_dtype {
 #define AA_FLAG_VMMA 64u         /* uint8 input: vertical pass on the tensor cores (tcgen05 kind::i8 + TMA, aa_vmma.cu);
                                     fails with AA_ERR_UNSUPPORTED if not eligible.  AUTO picks it for uint8 inputs
                                     downsampled >= 2x vertically                                      */
-#define AA_FLAG_STRICT_NONFINITE 128u /* propagate NaN/Inf exactly like the reference: an output is non-finite iff a tap with
-                                    index j < xsize of one of its two windows is (aa_interpolation_impl.h:73-85 never
-                                    touches j >= xsize).  The fast kernels multiply a few zero-weight neighbours past a
-                                    window (unrolled tap loops, accumulator slots not yet open), so with AUTO one NaN/Inf
-                                    pixel can also reach outputs whose window ends within K-1 taps before it; finite
-                                    inputs -- every image -- are unaffected.  This flag routes float inputs to the gather
-                                    kernel that touches in-window taps only (same arithmetic as AA_FLAG_FORCE_GENERAL);
-                                    uint8 inputs are always finite and keep their fast path.                      */
+/* NaN/Inf in float inputs.  The reference touches the taps j < xsize of a window and nothing else
+ * (aa_interpolation_impl.h:73-85): an output is non-finite iff one of ITS taps is.  The fast kernels also multiply a few
+ * zero-weight neighbours (unrolled tap loops, accumulators not yet open), so they check what they store; a CTA that stored
+ * a non-finite value lists its region and a second, tiny kernel behind every fast float launch re-evaluates the listed
+ * regions tap-exactly (csrc/aa_redo.cu).  With every path -- AUTO included -- the set of non-finite outputs is therefore
+ * the reference's; finite images pay an empty launch (a few microseconds), uint8 inputs nothing. */
+#define AA_FLAG_STRICT_NONFINITE 128u /* float inputs: the gather kernel that touches in-window taps only, i.e. the same
+                                    non-finite placement as AUTO and, in addition, finite values bit-identical to the
+                                    reference (same arithmetic as AA_FLAG_FORCE_GENERAL, at its speed)              */
+#define AA_FLAG_ASSUME_FINITE 256u /* the caller guarantees finite float data (e.g. converted uint8 images): skip the
+                                    drain launch -- one kernel per call.  If the data is not finite after all, a NaN/Inf
+                                    can also reach outputs whose window ends within K-1 taps of it; none is ever lost */
 #define AA_FLAG_ROUND_NEAREST 32u /* uint8 output: round to nearest (PIL) instead of truncating (.byte()) */
 
 /* A 4-D tensor view [n, c, h, w] with ELEMENT strides, resident on CUDA device `device`.

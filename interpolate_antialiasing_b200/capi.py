@@ -14,6 +14,7 @@ U8, F32, F64, F16, BF16 = 0, 1, 2, 3, 4
 FLAG_AUTO, FLAG_FORCE_GENERAL, FLAG_FORCE_STREAM, FLAG_STREAM_TMA, FLAG_STREAM_LDG, FLAG_ROUND_NEAREST = 0, 1, 2, 4, 8, 32
 FLAG_VMMA = 64
 FLAG_STRICT_NONFINITE = 128
+FLAG_ASSUME_FINITE = 256  # skip the drain launch behind the fast float kernels (csrc/aa_redo.cu)
 FILTERS = {"nearest": BOX, "box": BOX, "bilinear": TRIANGLE, "linear": TRIANGLE, "bicubic": CUBIC, "cubic": CUBIC}
 
 EXPORTS = [

@@ -155,6 +155,7 @@ int two_pass(const aa_tensor_desc* in, const aa_tensor_desc* out, const Layout& 
 int forward_impl(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter, int align, uint32_t flags,
                  cudaStream_t stream, const aa_epilogue* ex = nullptr, const aa_scales* sc = nullptr) {
   int rc;
+  const RedoScope redo_scope(!(flags & AA_FLAG_ASSUME_FINITE));
   if ((rc = check_desc(in, "input")) != AA_OK) return rc;
   if ((rc = check_desc(out, "output")) != AA_OK) return rc;
   if ((rc = check_filter(filter)) != AA_OK) return rc;
@@ -327,6 +328,10 @@ int aa_warm_tables(int64_t in_h, int64_t in_w, int64_t out_h, int64_t out_w, int
       rc = vmma_warm(th.get(), stream);
       if (rc != AA_OK && rc != AA_ERR_UNSUPPORTED) return rc;
     }
+    if (dtype != AA_U8) {  // float inputs: the stream's list of regions to redo tap-exactly (aa_redo.cu)
+      RedoList* rl = nullptr;
+      if ((rc = redo_list(device, stream, &rl)) != AA_OK) return rc;
+    }
   }
   // after this the tables are complete for every stream (and for CUDA-graph capture)
   AA_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -426,6 +431,7 @@ int aa_resize_forward_ragged(const aa_image_desc* images, int32_t count, int32_t
 static int backward_impl(const aa_tensor_desc* gout, const aa_tensor_desc* gin, int filter, int align_corners, uint32_t flags,
                          void* cuda_stream, const aa_scales* sc) {
   int rc;
+  const RedoScope redo_scope(!(flags & AA_FLAG_ASSUME_FINITE));
   Layout lo, li;
   if ((rc = check_filter(filter)) != AA_OK) return rc;
   if ((rc = backward_check(gout, gin, &lo, &li)) != AA_OK) return rc;

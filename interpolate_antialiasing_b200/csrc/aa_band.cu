@@ -53,6 +53,7 @@ struct BParams {
   int vec_load;    // rows of in are 16-byte aligned (f32) and whole 16-byte groups -> 16-byte cp.async
   FastDiv dci, dcp;  // division by Ci (flat column -> pixel) and by lin.Cp (plane -> image)
   int64_t plane0;  // first plane of this launch (planes are launched in slabs of <= 65535)
+  RedoList* redo;  // float input: where a CTA that stored a NaN/Inf reports its segment (aa_common.cuh)
 };
 
 template <typename in_t> __device__ __forceinline__ float ldf(const in_t* p) { return (float)__ldg(p); }
@@ -60,6 +61,7 @@ template <typename in_t> __device__ __forceinline__ float ldf(const in_t* p) { r
 template <int KH, int KW, bool GEN, typename in_t>
 __global__ void __launch_bounds__(NT) aa_band_kernel(const BParams P) {
   constexpr int HR = (KH + 1 + 3) / 4;  // float4 per row record {w[KH], first T row}
+  if constexpr (sizeof(in_t) == 4) aa_trigger_drain();
   extern __shared__ __align__(16) float smem[];
   const int TY = P.ty;
   float* Ts = smem;                                                       // [tr][TXF]
@@ -214,6 +216,8 @@ __global__ void __launch_bounds__(NT) aa_band_kernel(const BParams P) {
       coff[i] = P.epi.coloff(oxi, cch[i], Ci);
     }
   }
+  constexpr bool CHK = sizeof(in_t) == 4;  // float input can carry NaN/Inf (aa_common.cuh: aa_exact_region)
+  float4 chk = make_float4(0.f, 0.f, 0.f, 0.f);
   // T starts finite: rows past a window (zero weight) are read by the unrolled tap loop
   for (int r = 0; r < P.tr; r++) Ts[r * TXF + tid] = 0.f;
   store_rec(cA, rec);
@@ -274,6 +278,7 @@ __global__ void __launch_bounds__(NT) aa_band_kernel(const BParams P) {
           const float4 v = src[k * TXV];
           aa_fma4(a, v, rc[k]);
         }
+        if constexpr (CHK) aa_fma4(chk, a, 0.f);  // 0 * a stays 0 unless a holds a NaN/Inf
         if (!GEN && full && P.epi.kind == 0) {
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + dst + ofv) = a;
         } else if (!GEN && full && P.epi.kind == 1) {
@@ -293,6 +298,10 @@ __global__ void __launch_bounds__(NT) aa_band_kernel(const BParams P) {
     ra = ra_n;
     rb = rb_n;
     if (c + 2 < cB) extents(c + 2, ra_n, rb_n);
+  }
+  if constexpr (CHK) {  // once per segment: a non-finite value anywhere in it -> the drain kernel redoes it tap-exactly
+    if (__syncthreads_or(aa_nonfinite(chk.x + chk.y + chk.z + chk.w)) && tid == 0 && P.redo)
+      redo_push(P.redo, plane, -1, cA * TY, min(P.out_h, cB * TY), of0, of1);
   }
 }
 
@@ -408,8 +417,18 @@ int launch_band(const void* in, int in_dtype, const Layout& lin, void* out, cons
   P.dcp = FastDiv::make((uint32_t)(lin.Cp > 0 ? lin.Cp : 1));
   P.vec_store = (((uintptr_t)out) % (epi.kind == 1 ? 4 : 16) == 0) && (lout.stride_h % 4 == 0) && (lout.stride_n % 4 == 0) &&
                 (lout.Cp == 1 || lout.stride_p % 4 == 0);
-  const int rc = in_dtype == AA_F32 ? launch_in<float>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream, G)
-                                    : launch_in<uint8_t>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream, G);
+  P.redo = nullptr;
+  if (in_dtype == AA_F32) {
+    const int rl = redo_list(ah.device, stream, &P.redo);
+    if (rl != AA_OK) return rl;
+  }
+  int rc = in_dtype == AA_F32 ? launch_in<float>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream, G)
+                              : launch_in<uint8_t>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream, G);
+  if (rc == AA_OK && in_dtype == AA_F32 && lin.planes > 0) {
+    const RedoParams R{in, out, epi, lin, lout, Ci, ExactTabs{P.h_start, P.h_size, P.w_start, P.w_size, P.h_w, P.w_w, P.h_pitch, P.w_pitch},
+                       P.out_h, P.out_wf, 1, 0, P.redo};
+    rc = launch_redo(R, ah.device, stream);
+  }
   if (!planned && (rc == AA_OK || rc == AA_ERR_UNSUPPORTED) && lin.planes > 0) {
     if (rc == AA_ERR_UNSUPPORTED) G.ty = 0;
     geom_store(gkey, G);

@@ -150,8 +150,8 @@ namespace aa {
 // output column.  pb points at the column's first tap in patch row 0, taps are CI elements apart (CI = 0:
 // runtime interleave `ci`).  With a compile-time interleave the taps are immediate offsets of one row pointer,
 // so a row costs KW x (LDS + FFMA) + one address update instead of KW address updates.
-template <int KW, int CI>
-__device__ __forceinline__ void aa_hpass_rows(const float* pb, int pcp, int ci, const float (&w)[KW], float* dst, int tpitch, int n) {
+template <int KW, int CI, bool CHK>
+__device__ __forceinline__ void aa_hpass_rows(const float* pb, int pcp, int ci, const float (&w)[KW], float* dst, int tpitch, int n, float2& chk) {
   const int step = CI ? CI : ci;
   int r = 0;
   // two rows per step: packed FFMA2 (two fp32 FMAs per issue slot, the column's weight as the scalar operand)
@@ -161,6 +161,7 @@ __device__ __forceinline__ void aa_hpass_rows(const float* pb, int pcp, int ci, 
     float2 a = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < KW; k++) a = __ffma2_rn(make_float2(w[k], w[k]), make_float2(p[k * step], p[pcp + k * step]), a);
+    if constexpr (CHK) chk = __ffma2_rn(a, make_float2(0.f, 0.f), chk);  // 0 * a stays 0 unless a holds a NaN/Inf
     dst[r * tpitch] = a.x;
     dst[(r + 1) * tpitch] = a.y;
   }
@@ -169,6 +170,7 @@ __device__ __forceinline__ void aa_hpass_rows(const float* pb, int pcp, int ci, 
     float a = 0.f;
 #pragma unroll
     for (int k = 0; k < KW; k++) a = fmaf(p[k * step], w[k], a);
+    if constexpr (CHK) chk.x = fmaf(a, 0.f, chk.x);
     dst[r * tpitch] = a;
   }
 }
@@ -179,14 +181,22 @@ __device__ __forceinline__ void aa_fma4(float4& a, const float4& v, float w) {
   const float2 hi = __ffma2_rn(w2, make_float2(v.z, v.w), make_float2(a.z, a.w));
   a = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
+// CHK: `chk` collects 0 * (every value written to T): non-zero (NaN) iff one of them was NaN/Inf.  Every output of the
+// vertical pass is a finite combination of T values, so this is where the tile kernel looks for non-finite data: the
+// horizontal pass writes fewer values than the vertical pass stores whenever the gather upsamples.
+template <int KW, bool CHK = false>
+__device__ __forceinline__ void aa_hpass(const float* pb, int pcp, int ci, const float (&w)[KW], float* dst, int tpitch, int n, float2& chk) {
+  switch (ci) {  // warp-uniform
+    case 1: aa_hpass_rows<KW, 1, CHK>(pb, pcp, ci, w, dst, tpitch, n, chk); break;
+    case 3: aa_hpass_rows<KW, 3, CHK>(pb, pcp, ci, w, dst, tpitch, n, chk); break;
+    case 4: aa_hpass_rows<KW, 4, CHK>(pb, pcp, ci, w, dst, tpitch, n, chk); break;
+    default: aa_hpass_rows<KW, 0, CHK>(pb, pcp, ci, w, dst, tpitch, n, chk); break;
+  }
+}
 template <int KW>
 __device__ __forceinline__ void aa_hpass(const float* pb, int pcp, int ci, const float (&w)[KW], float* dst, int tpitch, int n) {
-  switch (ci) {  // warp-uniform
-    case 1: aa_hpass_rows<KW, 1>(pb, pcp, ci, w, dst, tpitch, n); break;
-    case 3: aa_hpass_rows<KW, 3>(pb, pcp, ci, w, dst, tpitch, n); break;
-    case 4: aa_hpass_rows<KW, 4>(pb, pcp, ci, w, dst, tpitch, n); break;
-    default: aa_hpass_rows<KW, 0>(pb, pcp, ci, w, dst, tpitch, n); break;
-  }
+  float2 none = make_float2(0.f, 0.f);
+  aa_hpass<KW, false>(pb, pcp, ci, w, dst, tpitch, n, none);
 }
 // exact unsigned division by a runtime constant (Granlund-Montgomery, branch-free): n / d for all n < 2^32
 struct FastDiv {
@@ -228,6 +238,87 @@ __device__ __forceinline__ void aa_store(void* base, int64_t idx, float v, int c
     }
   }
 }
+
+// ---- non-finite inputs: exact re-evaluation of an output region ---------------------------------------------
+// The reference touches the taps j < xsize of a window and nothing else (aa_interpolation_impl.h:73-85), so an
+// output is NaN/Inf iff one of ITS taps is.  The fast float kernels also multiply a few zero-weight neighbours
+// (unrolled tap loops, accumulators that are not open yet, the union window of a column pair): 0 * Inf = NaN would
+// leak into outputs whose own window is finite.  Every fast kernel therefore checks what it stores, and a CTA that
+// stored anything non-finite appends its region to a small per-stream list (RedoList).  A second, tiny kernel
+// (aa_redo.cu) follows every such launch: it reads the list's counter and exits -- about a microsecond -- unless
+// there are entries, which it re-evaluates with aa_exact_region: in-window taps only, horizontal then vertical like
+// the reference, straight from global memory.  (The redo used to live at the end of the fast kernels themselves:
+// even there, inlined or called, it cost the streaming kernel its load hoisting -- cfg2 0.88 -> 0.74 of peak -- and
+// the few-tap kernels registers.)  Finite images pay the check and the empty launch; an image with a NaN pays for the
+// regions that contain one.  uint8 inputs cannot be non-finite: no check, no second launch.
+struct ExactTabs {
+  const int32_t *h_start, *h_size, *w_start, *w_size;
+  const float *h_w, *w_w;
+  int h_pitch, w_pitch;
+};
+// first instruction of the fast float kernels: lets the drain kernel behind them (launched with programmatic stream
+// serialization, aa_redo.cu) become resident early; it still waits for this grid to complete before it reads anything
+__device__ __forceinline__ void aa_trigger_drain() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ bool aa_nonfinite(float v) { return !(fabsf(v) <= 3.402823466e38f); }
+template <bool GEN, typename in_t>
+__device__ __forceinline__ void aa_exact_region(const in_t* __restrict__ ip, int64_t in_sh, int Ci, ExactTabs T, void* out,
+                                             int64_t op, int64_t out_sh, const OutEpi& epi, int oy0, int oy1, int of0, int of1,
+                                             int tid, int nt) {
+  const int nf = of1 - of0;
+  const int total = (oy1 - oy0) * nf;
+  for (int i = tid; i < total; i += nt) {
+    const int r = i / nf, of = of0 + (i - r * nf), oy = oy0 + r;
+    const int ox = of / Ci, c = of - ox * Ci;
+    const int ys = T.h_start[oy], yn = T.h_size[oy], xs = T.w_start[ox], xn = T.w_size[ox];
+    const float* wy = T.h_w + (int64_t)oy * T.h_pitch;
+    const float* wx = T.w_w + (int64_t)ox * T.w_pitch;
+    const in_t* p = ip + (int64_t)ys * in_sh + (int64_t)xs * Ci + c;
+    float acc = 0.f;
+    for (int ky = 0; ky < yn; ky++, p += in_sh) {
+      float h = 0.f;
+      for (int kx = 0; kx < xn; kx++) h = fmaf((float)p[kx * Ci], wx[kx], h);
+      acc = fmaf(h, wy[ky], acc);
+    }
+    aa_store<GEN>(out, op + (int64_t)oy * out_sh + epi.coloff(ox, c, Ci), acc, c, epi);
+  }
+}
+// The per-(device, stream) list the fast kernels append to and the redo kernel drains (aa_redo.cu).
+constexpr int kRedoCap = 2040;  // 64 KB per list
+struct RedoEntry {
+  int64_t a, b;            // b < 0: rows [oy0, oy1) x flat columns [of0, of1) of plane a; else the streaming kernel's units [a, b)
+  int oy0, oy1, of0, of1;
+};
+struct RedoList {
+  unsigned int count, overflow, done, pad;  // overflow: more dirty regions than entries -> the whole output is redone
+  RedoEntry e[kRedoCap];
+};
+__device__ __forceinline__ void redo_push(RedoList* L, int64_t a, int64_t b, int oy0, int oy1, int of0, int of1) {
+  const unsigned int i = atomicAdd(&L->count, 1u);
+  if (i < (unsigned int)kRedoCap) L->e[i] = RedoEntry{a, b, oy0, oy1, of0, of1};
+  else L->overflow = 1u;
+}
+struct RedoParams {
+  const void* in;  // float
+  void* out;
+  OutEpi epi;
+  Layout lin, lout;
+  int Ci;
+  ExactTabs T;
+  int out_h, out_wf;      // output rows, flat output columns
+  int n_strips, strip_ox; // streaming kernel's unit decode (units entries only)
+  RedoList* list;
+};
+// the calling stream's list (host bookkeeping once the device has a chunk of lists: aa_redo.cu)
+int redo_list(int device, cudaStream_t stream, RedoList** out);
+// the drain kernel, right behind the fast kernel on the same stream
+int launch_redo(const RedoParams& R, int device, cudaStream_t stream);
+void redo_clear();  // frees every list (aa_clear_table_cache)
+bool redo_set_enabled(bool on);  // this thread's launches: returns the previous setting
+struct RedoScope {                // AA_FLAG_ASSUME_FINITE: no drain launch for the calls made inside the scope
+  bool was;
+  explicit RedoScope(bool on) : was(redo_set_enabled(on)) {}
+  ~RedoScope() { redo_set_enabled(was); }
+};
 }  // namespace aa
 #endif
 namespace aa {

@@ -48,6 +48,7 @@ namespace {
 template <int A, int VEC, typename in_t, int NT, int U, int MINB, bool GEN, bool PAD, bool PF = true>
 __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
   extern __shared__ __align__(16) float smem[];
+  if constexpr (sizeof(in_t) == 4) aa_trigger_drain();
   constexpr int RPT = 4;
   constexpr int VW = NT * VEC;  // row pitch of Vs in floats (== P.vw)  // rows per thread in the horizontal phase
   constexpr int RS4 = (A + 1 + 3) / 4;  // float4 per row record
@@ -66,6 +67,9 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
   const int64_t u_end = P.total_units * (int64_t)(blockIdx.x + 1) / gridDim.x;
   int cur_strip = -1, strip_fl0 = 0, strip_npc = 0;
   HRole role = {0, 1, 0, 1};
+  constexpr bool CHK = sizeof(in_t) == 4;  // float input can carry NaN/Inf (aa_common.cuh: aa_exact_region)
+  __shared__ int s_bad;                    // some thread stored a non-finite value (in shared memory, not a register: the
+  if (t == 0) s_bad = 0;                   // 64-register shapes have none to spare; ordered by the strip-setup barrier)
 
   for (int64_t u = u_begin; u < u_end;) {
     // ---- segment = run of output rows [oyA, oyB) inside one (plane, strip) column
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
     // horizontal filter over the buffered rows [gbase, gbase+cnt)
     auto hphase = [&]() {
       __syncthreads();
-      hphase_run<RPT, VW, GEN, PAD>(P, Vs, Wp, pinfo, op, strip_npc, role, gbase, cnt);
+      if (hphase_run<RPT, VW, GEN, PAD, CHK>(P, Vs, Wp, pinfo, op, strip_npc, role, gbase, cnt)) s_bad = 1;
       __syncthreads();
       gbase += cnt;
       cnt = 0;
@@ -197,6 +201,10 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_kernel(const SParams P) {
     }
     if (cnt > 0) hphase();
     u = seg_end;
+  }
+  if constexpr (CHK) {  // (every write of s_bad is followed by a barrier of its horizontal phase; the unit range is
+    if (threadIdx.x == 0 && s_bad && P.redo)  // recomputed so that nothing of it stays live through the loop)
+      redo_push(P.redo, P.total_units * (int64_t)blockIdx.x / gridDim.x, P.total_units * (int64_t)(blockIdx.x + 1) / gridDim.x, 0, 0, 0, 0);
   }
 }
 
@@ -375,7 +383,19 @@ int launch_stream(const void* in, int in_dtype, const Layout& lin, void* out, co
   P.xmin_h = th->xmin; P.xsize_h = th->xsize;
   P.xmin_w = tw->xmin; P.xsize_w = tw->xsize; P.w_w = (const float*)tw->w; P.Kw = tw->K;
   const StreamTables T{th->id, tw->id, 0, th->h_xmin.data(), th->h_xsize.data(), oH, tw->h_xmin.data(), tw->h_xsize.data(), W, oW};
-  return dispatch_A(P, A, in_dtype, vec, T, th->device, flags, stream);
+  P.redo = nullptr;
+  if (in_dtype == AA_F32) {
+    rc = redo_list(th->device, stream, &P.redo);
+    if (rc != AA_OK) return rc;
+  }
+  rc = dispatch_A(P, A, in_dtype, vec, T, th->device, flags, stream);
+  if (rc == AA_OK && in_dtype == AA_F32) {  // drain kernel: tap-exact redo of what stored a NaN/Inf (aa_redo.cu)
+    const RedoParams R{in, out, epi, lin, lout, lin.Ci,
+                       ExactTabs{P.xmin_h, P.xsize_h, P.xmin_w, P.xsize_w, (const float*)th->w, P.w_w, th->K, P.Kw},
+                       (int)oH, (int)(oW * lin.Ci), P.n_strips, P.strip_ox, P.redo};
+    rc = launch_redo(R, th->device, stream);
+  }
+  return rc;
 }
 
 int launch_stream_adjoint(const void* gout, const Layout& lo, void* gin, const Layout& li, AxisTables* th, AxisTables* tw,
@@ -401,7 +421,16 @@ int launch_stream_adjoint(const void* gout, const Layout& lo, void* gin, const L
   P.xmin_h = th->omin; P.xsize_h = th->osize;
   P.xmin_w = tw->omin; P.xsize_w = tw->osize; P.w_w = (const float*)tw->wT; P.Kw = tw->KT;
   const StreamTables T{th->id, tw->id, 1, th->h_omin.data(), th->h_osize.data(), H, tw->h_omin.data(), tw->h_osize.data(), oW, W};
-  return dispatch_A(P, A, AA_F32, vec, T, th->device, 0u, stream);
+  rc = redo_list(th->device, stream, &P.redo);
+  if (rc != AA_OK) return rc;
+  rc = dispatch_A(P, A, AA_F32, vec, T, th->device, 0u, stream);
+  if (rc == AA_OK) {
+    const RedoParams R{gout, gin, P.epi, lo, li, lo.Ci,
+                       ExactTabs{P.xmin_h, P.xsize_h, P.xmin_w, P.xsize_w, (const float*)th->wT, P.w_w, th->KT, P.Kw},
+                       (int)H, (int)(W * lo.Ci), P.n_strips, P.strip_ox, P.redo};
+    rc = launch_redo(R, th->device, stream);
+  }
+  return rc;
 }
 
 }  // namespace aa

@@ -25,6 +25,7 @@ struct SParams {
   const int32_t *xmin_w, *xsize_w;
   const float* w_w;  // [oW][Kw]
   int Kw;
+  RedoList* redo;  // float input: where a CTA that stored a NaN/Inf reports its unit range (aa_common.cuh)
   int n_strips, strip_ox;
   int64_t total_units;  // planes * n_strips * oH
   int vw;               // columns of a Vs row (strip capacity); the row pitch is vs_pitch(vw)
@@ -218,12 +219,13 @@ __device__ __forceinline__ void strip_setup(const SParams& P, int t, int nthread
 // Gather over the buffered rows [0, cnt) of Vs -> output rows gbase..gbase+cnt-1.  Trip counts are
 // warp-uniform (longest union window in the warp); past a lane's own window the weights read are the
 // zero padding and the data pointer stops advancing, so no element outside the true windows is touched.
-template <int RPT, int VW, bool GEN, bool PAD>
-__device__ __forceinline__ void hphase_run_pairs(const float* __restrict__ Vs, const float2* __restrict__ Wp,
+template <int RPT, int VW, bool GEN, bool PAD, bool CHK>
+__device__ __forceinline__ bool hphase_run_pairs(const float* __restrict__ Vs, const float2* __restrict__ Wp,
                                            const int4* __restrict__ pinfo, void* __restrict__ op, int64_t op_off,
                                            const OutEpi& epi, int64_t out_stride_h, int Ci, int npc, const HRole role, int gbase,
                                            int cnt, int padsh) {
   const int nrg = (cnt + RPT - 1) / RPT;
+  bool bad = false;  // CHK: a non-finite value was stored (the caller redoes the rows tap-exactly, aa_common.cuh)
   for (int rg = role.rg0; rg < nrg; rg += role.rg_par) {
     for (int cfb = role.cf0 - (role.cf0 & 31); cfb < npc; cfb += role.cf_step) {
       const int pc = cfb + (role.cf0 & 31);
@@ -258,6 +260,7 @@ __device__ __forceinline__ void hphase_run_pairs(const float* __restrict__ Vs, c
 #pragma unroll
         for (int r = 0; r < RPT; r++) {
           if (rg * RPT + r < cnt) {
+            if constexpr (CHK) bad |= aa_nonfinite(h[r].x + h[r].y);
             aa_store<GEN>(op, dst + (int64_t)r * out_stride_h, h[r].x, c, epi);
             if (hasb) aa_store<GEN>(op, dst + (int64_t)r * out_stride_h + cstep, h[r].y, c, epi);
           }
@@ -265,14 +268,16 @@ __device__ __forceinline__ void hphase_run_pairs(const float* __restrict__ Vs, c
       }
     }
   }
+  return bad;
 }
 // single-column form (P.pairs == 0): one item = one flat output column x RPT rows, FFMA2 over row pairs
-template <int RPT, int VW, bool GEN, bool PAD>
-__device__ __forceinline__ void hphase_run_single(const float* __restrict__ Vs, const float* __restrict__ Ws,
+template <int RPT, int VW, bool GEN, bool PAD, bool CHK>
+__device__ __forceinline__ bool hphase_run_single(const float* __restrict__ Vs, const float* __restrict__ Ws,
                                                   const int4* __restrict__ pinfo, void* __restrict__ op, int64_t op_off,
                                                   const OutEpi& epi, int64_t out_stride_h, int Ci, int nof, const HRole role,
                                                   int gbase, int cnt, int padsh) {
   const int nrg = (cnt + RPT - 1) / RPT;
+  bool bad = false;
   for (int rg = role.rg0; rg < nrg; rg += role.rg_par) {
     for (int cfb = role.cf0 - (role.cf0 & 31); cfb < nof; cfb += role.cf_step) {
       const int cf = cfb + (role.cf0 & 31);
@@ -307,17 +312,21 @@ __device__ __forceinline__ void hphase_run_single(const float* __restrict__ Vs, 
         const int c = ci.z >> 20;
 #pragma unroll
         for (int r = 0; r < RPT; r++)
-          if (rg * RPT + r < cnt) aa_store<GEN>(op, dst + (int64_t)r * out_stride_h, h[r], c, epi);
+          if (rg * RPT + r < cnt) {
+            if constexpr (CHK) bad |= aa_nonfinite(h[r]);
+            aa_store<GEN>(op, dst + (int64_t)r * out_stride_h, h[r], c, epi);
+          }
       }
     }
   }
+  return bad;
 }
-template <int RPT, int VW, bool GEN, bool PAD>
-__device__ __forceinline__ void hphase_run(const SParams& P, const float* Vs, const float2* Wp, const int4* pinfo, int64_t op_off,
+template <int RPT, int VW, bool GEN, bool PAD, bool CHK>
+__device__ __forceinline__ bool hphase_run(const SParams& P, const float* Vs, const float2* Wp, const int4* pinfo, int64_t op_off,
                                            int npc, const HRole role, int gbase, int cnt) {
   const int padsh = P.pad == 4 ? 4 : P.pad == 2 ? 3 : 2;  // byte shift of (f >> 5) * q
-  if (P.pairs) hphase_run_pairs<RPT, VW, GEN, PAD>(Vs, Wp, pinfo, P.out, op_off, P.epi, P.lout.stride_h, P.Ci, npc, role, gbase, cnt, padsh);
-  else hphase_run_single<RPT, VW, GEN, PAD>(Vs, reinterpret_cast<const float*>(Wp), pinfo, P.out, op_off, P.epi, P.lout.stride_h, P.Ci, npc, role, gbase, cnt, padsh);
+  if (P.pairs) return hphase_run_pairs<RPT, VW, GEN, PAD, CHK>(Vs, Wp, pinfo, P.out, op_off, P.epi, P.lout.stride_h, P.Ci, npc, role, gbase, cnt, padsh);
+  return hphase_run_single<RPT, VW, GEN, PAD, CHK>(Vs, reinterpret_cast<const float*>(Wp), pinfo, P.out, op_off, P.epi, P.lout.stride_h, P.Ci, npc, role, gbase, cnt, padsh);
 }
 // bytes of the strip tables (after Vs) for a plan
 inline size_t strip_table_bytes(const SParams& P) {

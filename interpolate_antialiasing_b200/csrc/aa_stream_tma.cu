@@ -84,7 +84,9 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
 
   const int t = threadIdx.x;
   const int warp = t >> 5, lane = t & 31;
+  __shared__ int s_bad;  // some consumer stored a non-finite value
   if (t == 0) {
+    s_bad = 0;
     for (int i = 0; i < STAGES; i++) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, NWC); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -132,6 +134,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
   }
 
   // =============================== consumers ========================================================
+  constexpr bool CHK = sizeof(in_t) == 4;  // float input can carry NaN/Inf (aa_common.cuh: aa_exact_region)
   constexpr int vw = VW;
   int cur_strip = -1, strip_fl0 = 0, strip_npc = 0;
   HRole role = {0, 1, 0, 1};
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
     };
     auto hphase = [&]() {
       consumer_sync();
-      hphase_run<RPT, VW, false, false>(P, Vs, Wp, pinfo, op, strip_npc, role, gbase, cnt);
+      if (hphase_run<RPT, VW, false, false, CHK>(P, Vs, Wp, pinfo, op, strip_npc, role, gbase, cnt)) s_bad = 1;
       consumer_sync();
       gbase += cnt;
       cnt = 0;
@@ -235,6 +238,9 @@ __global__ void __launch_bounds__(NT, MINB) aa_stream_tma_kernel(const SParams P
       if (cnt >= P.tg || (y + R >= yB && cnt > 0)) hphase();
     }
     u = seg_end;
+  }
+  if constexpr (CHK) {
+    if (t == 0 && s_bad && P.redo) redo_push(P.redo, u_begin, u_end, 0, 0, 0, 0);
   }
 }
 

@@ -641,6 +641,7 @@ int clear_table_cache() {
   stream_detail::plan_clear();
   vmma_plan_clear();
   tile_plan_clear();
+  redo_clear();
   std::map<Key, std::shared_ptr<AxisTables>> old;
   {
     std::lock_guard<std::mutex> lock(g_mu);

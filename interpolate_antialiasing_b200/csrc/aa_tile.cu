@@ -50,6 +50,7 @@ struct TParams {
   int vec_load;   // rows of in are 16-byte aligned (f32) -> 16-byte cp.async in stage 0
   FastDiv dci, dcp;  // division by Ci (flat column -> pixel) and by lin.Cp (plane -> image)
   int64_t plane0;  // first plane of this launch (planes are launched in slabs of <= 65535)
+  RedoList* redo;  // float input: where a CTA that stored a NaN/Inf reports its tile (aa_common.cuh)
 };
 
 template <typename in_t> __device__ __forceinline__ float ldf(const in_t* p) { return (float)__ldg(p); }
@@ -69,9 +70,13 @@ template <int KH, int VR> struct VRec {
 };
 
 template <int KH, int KW, int VR, bool GEN, typename in_t>
-__global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
+// register caps = what the kernels used before the NaN/Inf check was added (32 for the 2-3 tap shapes, whose small
+// tiles fit 7 CTAs per SM; 40-48 for the others): left alone, ptxas takes ~48 for all of them and the 2-3 tap shapes
+// lose two CTAs per SM (bilinear 2x upsampling 180 -> 199 us)
+__global__ void __launch_bounds__(NT, GEN ? 2 : (KH <= 3 && VR == 1 ? 8 : 5)) aa_tile_kernel(const TParams P) {
   using R = VRec<KH, VR>;
   constexpr int HR = R::HR;
+  if constexpr (sizeof(in_t) == 4) aa_trigger_drain();
   const int TY = P.ty;
   extern __shared__ __align__(16) float smem[];
   float* Ts = smem;                                                   // [tr][TXF]
@@ -222,10 +227,16 @@ __global__ void __launch_bounds__(NT) aa_tile_kernel(const TParams P) {
   if constexpr (sizeof(in_t) == 4) asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   // ---- stage 1: horizontal pass -> Ts
-  aa_hpass<KW>(patch + soff, P.pcp, Ci, w, Ts + tid, TXF, nr);
+  constexpr bool CHK = sizeof(in_t) == 4;  // float input can carry NaN/Inf (aa_common.cuh: aa_exact_region)
+  float2 chk = make_float2(0.f, 0.f);
+  aa_hpass<KW, CHK>(patch + soff, P.pcp, Ci, w, Ts + tid, TXF, nr, chk);
 #pragma unroll
   for (int r = 0; r < R::ZR; r++) Ts[(nr + r) * TXF + tid] = 0.f;  // rows past the last window: zero weight, finite value
-  __syncthreads();
+  if constexpr (CHK) {  // a non-finite value went into T: the drain kernel redoes this tile tap-exactly (aa_common.cuh)
+    if (__syncthreads_or(aa_nonfinite(chk.x + chk.y)) && tid == 0 && P.redo) redo_push(P.redo, plane, -1, oy0, oy1, of0, of1);
+  } else {
+    __syncthreads();
+  }
   // ---- stage 2: vertical pass + store
   const int ofv = of0 + 4 * tx;
   if (ofv < of1) {
@@ -456,8 +467,18 @@ int launch_tile(const void* in, int in_dtype, const Layout& lin, void* out, cons
   P.dcp = FastDiv::make((uint32_t)(lin.Cp > 0 ? lin.Cp : 1));
   P.vec_store = (((uintptr_t)out) % (epi.kind == 1 ? 4 : 16) == 0) && (lout.stride_h % 4 == 0) && (lout.stride_n % 4 == 0) &&
                 (lout.Cp == 1 || lout.stride_p % 4 == 0);
-  const int rc = in_dtype == AA_F32 ? launch_in<float>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream, G)
-                                    : launch_in<uint8_t>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream, G);
+  P.redo = nullptr;
+  if (in_dtype == AA_F32) {
+    const int rl = redo_list(ah.device, stream, &P.redo);
+    if (rl != AA_OK) return rl;
+  }
+  int rc = in_dtype == AA_F32 ? launch_in<float>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream, G)
+                              : launch_in<uint8_t>(P, kh_max, kw_max, lin.planes, ah, (int)nc, stream, G);
+  if (rc == AA_OK && in_dtype == AA_F32 && lin.planes > 0) {
+    const RedoParams R{in, out, epi, lin, lout, Ci, ExactTabs{P.h_start, P.h_size, P.w_start, P.w_size, P.h_w, P.w_w, P.h_pitch, P.w_pitch},
+                       P.out_h, P.out_wf, 1, 0, P.redo};
+    rc = launch_redo(R, ah.device, stream);
+  }
   if (!planned && (rc == AA_OK || rc == AA_ERR_UNSUPPORTED) && lin.planes > 0) {
     if (rc == AA_ERR_UNSUPPORTED) G.ty = 0;
     geom_store(gkey, G);

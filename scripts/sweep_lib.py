@@ -57,8 +57,8 @@ def run_point(p, torch, capi, dev, gen, peak, dist=None, world=1, flags=0, min_b
     if p["cl"]:
         x = x.contiguous(memory_format=torch.channels_last)
     if p["group"] == "bwd":
-        out = capi.resize_backward(x, (N, C, HIN, WIN), p["mode"], False)
-        call = lambda: capi.resize_backward(x, (N, C, HIN, WIN), p["mode"], False, out=out)
+        out = capi.resize_backward(x, (N, C, HIN, WIN), p["mode"], False, flags=flags)
+        call = lambda: capi.resize_backward(x, (N, C, HIN, WIN), p["mode"], False, flags=flags, out=out)
     else:
         out = capi.resize_forward(x, (oh, ow), p["mode"], False, flags)
         call = lambda: capi.resize_forward(x, (oh, ow), p["mode"], False, flags, out=out)

@@ -154,17 +154,16 @@ def test_named_config_slices(cuda):
 
 
 def test_nonfinite_placement_tile_band_stream(cuda):
-    """NaN/Inf pixels in every kernel regime (tile: upsampling; band: 0.75x; stream: downsampling), reference
-    aa_interpolation_impl.h:73-85 (only taps j < xsize are touched):
-      * AA_FLAG_STRICT_NONFINITE and AA_FLAG_FORCE_GENERAL: the set of non-finite outputs equals the oracle's exactly and
-        the finite ones are bit-identical;
-      * AUTO (fast kernels): no non-finite output is LOST (every output the oracle makes non-finite is non-finite), the
-        finite outputs the oracle and the kernel agree on are within tolerance, and the extra spread stays inside the
-        documented halo of K-1 taps per axis (include/aa_resize.h, AA_FLAG_STRICT_NONFINITE)."""
+    """NaN/Inf pixels in every kernel regime (tile: upsampling; band: 0.75x; stream: downsampling; two launches: mixed),
+    reference aa_interpolation_impl.h:73-85 (only taps j < xsize are touched, so an output is non-finite iff one of ITS
+    taps is).  On EVERY path -- the fast kernels (AUTO: they check what they store and redo a region tap-exactly,
+    aa_common.cuh aa_exact_region), AA_FLAG_STRICT_NONFINITE and AA_FLAG_FORCE_GENERAL -- the set of non-finite outputs
+    equals the oracle's exactly; the finite ones are within tolerance on the fast path and bit-identical on the other two."""
     from interpolate_antialiasing_b200 import capi
     g = torch.Generator().manual_seed(17)
     for (H, W), osize, mode in [((40, 60), (80, 120), "cubic"), ((64, 96), (48, 72), "cubic"), ((64, 96), (48, 72), "linear"),
-                                ((120, 160), (30, 40), "linear"), ((120, 160), (24, 50), "cubic"), ((50, 70), (50, 70), "linear")]:
+                                ((120, 160), (30, 40), "linear"), ((120, 160), (24, 50), "cubic"), ((50, 70), (50, 70), "linear"),
+                                ((96, 64), (40, 150), "cubic"), ((64, 96), (100, 30), "linear"), ((300, 420), (37, 53), "cubic")]:
         x = torch.rand((2, 3, H, W), generator=g) * 255
         for (n, c, y, xx), val in [((0, 0, 5, 7), float("nan")), ((0, 2, H - 1, W - 1), float("inf")), ((1, 1, H // 2, W // 3), float("-inf")),
                                    ((1, 0, 0, 0), float("nan"))]:
@@ -173,23 +172,36 @@ def test_nonfinite_placement_tile_band_stream(cuda):
             xc = x.to(cuda).contiguous(memory_format=torch.channels_last) if cl else x.to(cuda)
             want = O.forward(x.numpy(), osize, mode, False)
             wbad = ~np.isfinite(want)
+            assert wbad.any() and not wbad.all()
             for flags in (capi.FLAG_STRICT_NONFINITE, capi.FLAG_FORCE_GENERAL):
                 y = _run(capi, xc, osize, mode, False, flags).cpu().numpy()
                 assert np.array_equal(~np.isfinite(y), wbad), (H, W, osize, mode, cl, flags)
                 assert np.array_equal(y[~wbad], want[~wbad])
-            y = _run(capi, xc, osize, mode, False, capi.FLAG_AUTO).cpu().numpy()
+            for flags in (capi.FLAG_AUTO, capi.FLAG_FORCE_STREAM):
+                if flags == capi.FLAG_FORCE_STREAM and osize[0] > H:
+                    continue  # the streaming kernel does not upsample in H
+                y = _run(capi, xc, osize, mode, False, flags).cpu().numpy()
+                assert np.array_equal(~np.isfinite(y), wbad), (H, W, osize, mode, cl, flags)
+                _close(y[~wbad], want[~wbad])
+            # AA_FLAG_ASSUME_FINITE (no drain launch): nothing is lost, and what spreads stays within K-1 taps per axis
+            y = _run(capi, xc, osize, mode, False, capi.FLAG_ASSUME_FINITE).cpu().numpy()
             ybad = ~np.isfinite(y)
             assert not np.any(wbad & ~ybad), "a non-finite output was lost"
-            both = ~wbad & ~ybad
-            _close(y[both], want[both])
-            # spread: every extra non-finite output lies within K-1 rows / columns of an oracle one (same plane)
-            # K-1 INPUT taps past a window = that many output pixels when downsampling, (K-1)*out/in of them when upsampling
+            _close(y[~wbad & ~ybad], want[~wbad & ~ybad])
             Kh = int(np.ceil((capi.interp_size(H, osize[0], mode) - 1) * max(1.0, osize[0] / H))) + 1
             Kw = int(np.ceil((capi.interp_size(W, osize[1], mode) - 1) * max(1.0, osize[1] / W))) + 1
-            extra = np.argwhere(ybad & ~wbad)
-            for (n, c, oy, ox) in extra:
-                win = wbad[n, c, max(0, oy - Kh):oy + Kh + 1, max(0, ox - Kw):ox + Kw + 1]
-                assert win.any(), (H, W, osize, mode, cl, (n, c, oy, ox))
+            for (n, c, oy, ox) in np.argwhere(ybad & ~wbad):
+                assert wbad[n, c, max(0, oy - Kh):oy + Kh + 1, max(0, ox - Kw):ox + Kw + 1].any(), (H, W, osize, mode, cl, (n, c, oy, ox))
+            # the adjoint kernels (backward): grad_in is non-finite iff a grad_out element whose window holds it is
+            gy = torch.rand((2, 3) + tuple(osize), generator=g)
+            gy[0, 1, osize[0] // 2, osize[1] // 2] = float("nan")
+            gy[1, 2, 0, osize[1] - 1] = float("inf")
+            gyc = gy.to(cuda).contiguous(memory_format=torch.channels_last) if cl else gy.to(cuda)
+            gwant = O.backward_adjoint(gy.numpy(), (2, 3, H, W), mode, False)
+            gbad = ~np.isfinite(gwant)
+            gx = capi.resize_backward(gyc, (2, 3, H, W), mode, False).cpu().numpy()
+            assert np.array_equal(~np.isfinite(gx), gbad), (H, W, osize, mode, cl, "backward")
+            assert np.allclose(gx[~gbad], gwant[~gbad], rtol=1e-5, atol=4e-6)
 
 
 def test_cfg3_eight_images_all_paths(cuda):

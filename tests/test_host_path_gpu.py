@@ -55,7 +55,14 @@ def test_table_cache_clear_and_rebuild(cuda):
     a = capi.resize_forward(x, (20, 30), "cubic")
     n0 = capi.launch_count(reset=True)
     b = capi.resize_forward(x, (20, 30), "cubic")
-    assert capi.launch_count(reset=True) == 1 and n0 >= 1          # warm cache: exactly one kernel launch per call
+    assert capi.launch_count(reset=True) == 2 and n0 >= 2          # warm cache: the kernel + the drain kernel behind it (aa_redo.cu)
+    d = capi.resize_forward(x, (20, 30), "cubic", flags=capi.FLAG_ASSUME_FINITE)
+    assert capi.launch_count(reset=True) == 1                      # ... which AA_FLAG_ASSUME_FINITE leaves out
+    capi.resize_forward(x.byte(), (20, 30), "cubic")                 # (first uint8 call: derived tables of the tensor-core path)
+    capi.launch_count(reset=True)
+    capi.resize_forward(x.byte(), (20, 30), "cubic")
+    assert capi.launch_count(reset=True) == 1                      # uint8 cannot hold a NaN: one launch
+    assert torch.equal(b, d)
     assert capi.lib().aa_clear_table_cache() == 0
     c = capi.resize_forward(x, (20, 30), "cubic")
     assert capi.launch_count(reset=True) >= 3                        # tables rebuilt (fwd + adjoint kernels per axis) + the op
