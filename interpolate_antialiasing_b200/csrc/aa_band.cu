@@ -50,7 +50,7 @@ struct BParams {
   int tr;          // T rows (pr + KH - 1: the unrolled tap loop may read up to KH-1 rows past a window, with zero weight)
   int pcp;         // patch pitch in floats (multiple of 4)
   int vec_store;   // rows of out are 16-byte aligned -> float4 stores
-  int vec_load;    // rows of in are 16-byte aligned (f32) and whole 16-byte groups -> 16-byte cp.async
+  int vec_load;    // rows of in are 16-byte (f32) / 4-byte (u8) aligned and whole 4-element groups -> 16-byte cp.async / 32-bit loads
   FastDiv dci, dcp;  // division by Ci (flat column -> pixel) and by lin.Cp (plane -> image)
   int64_t plane0;  // first plane of this launch (planes are launched in slabs of <= 65535)
   RedoList* redo;  // float input: where a CTA that stored a NaN/Inf reports its segment (aa_common.cuh)
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(NT) aa_band_kernel(const BParams P) {
   const int c0 = __ldg(P.w_start + oxa) * Ci, c1 = (__ldg(P.w_start + oxb) + __ldg(P.w_size + oxb)) * Ci;
   const int nc = c1 - c0;
   const int pct = nc + (KW - 1) * Ci;  // patch columns touched by the unrolled tap loop
-  const bool vload = sizeof(in_t) == 4 && P.vec_load;
+  const bool vload = P.vec_load != 0;
   const int lead = vload ? (c0 & 3) : 0;  // aligned patches start `lead` columns early
   const int pcp = P.pcp;
   const int64_t sh = P.lin.stride_h;
@@ -134,6 +134,32 @@ __global__ void __launch_bounds__(NT) aa_band_kernel(const BParams P) {
       asm volatile("cp.async.commit_group;" ::: "memory");
     } else {
       // uint8: through registers (converted once here, not per tap), 4 loads in flight per thread
+      if (vload) {
+        // rows 4-byte aligned and made of whole 4-pixel groups: one 32-bit load = 4 pixels -> one 128-bit shared store
+        const int nq = (lead + pct + 3) >> 2;                       // groups the tap loops may touch
+        const int nql = min(nq, (P.in_wf - (c0 - lead)) >> 2);      // groups that exist in the row
+        for (int r = warp; r < n; r += NWARP) {
+          const in_t* srow = src + (int64_t)r * sh;
+          float* drow = pb + r * pcp;
+          for (int qb = lane; qb < nq; qb += 128) {
+            uint32_t wv[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const int q = qb + 32 * j;
+              wv[j] = q < nql ? __ldg(reinterpret_cast<const uint32_t*>(srow) + q) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const int q = qb + 32 * j;
+              if (q < nq) {
+                float f[4];
+                aa_unpack4(wv[j], f);
+                *reinterpret_cast<float4*>(drow + 4 * q) = make_float4(f[0], f[1], f[2], f[3]);
+              }
+            }
+          }
+        }
+      } else
       for (int r = warp; r < n; r += NWARP) {
         const in_t* srow = src + (int64_t)r * sh;
         float* drow = pb + r * pcp;
@@ -411,7 +437,7 @@ int launch_band(const void* in, int in_dtype, const Layout& lin, void* out, cons
       return fail(AA_ERR_UNSUPPORTED, "band: input patch too large; use the streaming/general path");
     }
   }
-  P.vec_load = in_dtype == AA_F32 && ((uintptr_t)in) % 16 == 0 && lin.stride_h % 4 == 0 && lin.stride_n % 4 == 0 &&
+  P.vec_load = ((uintptr_t)in) % (in_dtype == AA_F32 ? 16 : 4) == 0 && lin.stride_h % 4 == 0 && lin.stride_n % 4 == 0 &&
                (lin.Cp == 1 || lin.stride_p % 4 == 0) && P.in_wf % 4 == 0;
   P.dci = FastDiv::make((uint32_t)Ci);
   P.dcp = FastDiv::make((uint32_t)(lin.Cp > 0 ? lin.Cp : 1));

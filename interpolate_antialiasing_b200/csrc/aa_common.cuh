@@ -174,6 +174,17 @@ __device__ __forceinline__ void aa_hpass_rows(const float* pb, int pcp, int ci, 
     dst[r * tpitch] = a;
   }
 }
+// uint8 -> float without the conversion unit (I2F runs on the 16-lane XU pipe): PRMT drops the byte
+// into the mantissa of 2^23 (0x4B0000bb == 8388608 + b exactly) and a packed FADD2 removes the bias of two
+// elements at once (the pairs are the ones the FFMA2 of the vertical pass consumes).
+__device__ __forceinline__ void aa_unpack4(uint32_t w, float* v) {
+  const float2 nb = make_float2(-8388608.0f, -8388608.0f);
+  const float2 lo = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)),
+                                           __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541))), nb);
+  const float2 hi = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)),
+                                           __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543))), nb);
+  v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
+}
 // Vertical taps of the few-tap kernels: a += w * v for 4 adjacent columns (two FFMA2)
 __device__ __forceinline__ void aa_fma4(float4& a, const float4& v, float w) {
   const float2 w2 = make_float2(w, w);

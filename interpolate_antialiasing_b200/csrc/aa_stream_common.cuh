@@ -80,17 +80,7 @@ template <> struct VLoad<uint8_t, 4> {
     asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r[0]) : "l"(p));
   }
 };
-// uint8 -> float without the conversion unit (I2F runs on the 16-lane XU pipe): PRMT drops the byte
-// into the mantissa of 2^23 (0x4B0000bb == 8388608 + b exactly) and a packed FADD2 removes the bias of two
-// elements at once (the pairs are the ones the FFMA2 of the vertical pass consumes).
-__device__ __forceinline__ void unpack4(uint32_t w, float* v) {
-  const float2 nb = make_float2(-8388608.0f, -8388608.0f);
-  const float2 lo = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)),
-                                           __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541))), nb);
-  const float2 hi = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)),
-                                           __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543))), nb);
-  v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
-}
+__device__ __forceinline__ void unpack4(uint32_t w, float* v) { aa_unpack4(w, v); }  // aa_common.cuh
 template <int VEC> __device__ __forceinline__ void expand(const float (&r)[VEC], float (&v)[VEC]) {
 #pragma unroll
   for (int i = 0; i < VEC; i++) v[i] = r[i];

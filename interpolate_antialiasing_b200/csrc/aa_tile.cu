@@ -47,7 +47,7 @@ struct TParams {
   int tr;    // T rows: pr + the zero rows the unrolled vertical tap loop may touch past the last window
   int pcp;   // patch pitch in floats (max input flat cols per tile + (KW-1)*Ci, padded)
   int vec_store;  // rows of out are 16-byte aligned -> float4 stores
-  int vec_load;   // rows of in are 16-byte aligned (f32) -> 16-byte cp.async in stage 0
+  int vec_load;   // rows of in are 16-byte (f32) / 4-byte (u8) aligned -> 16-byte cp.async / 32-bit loads in stage 0
   FastDiv dci, dcp;  // division by Ci (flat column -> pixel) and by lin.Cp (plane -> image)
   int64_t plane0;  // first plane of this launch (planes are launched in slabs of <= 65535)
   RedoList* redo;  // float input: where a CTA that stored a NaN/Inf reports its tile (aa_common.cuh)
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(NT, GEN ? 2 : (KH <= 3 && VR == 1 ? 8 : 5)) aa
   const int c0 = __ldg(P.w_start + oxa) * Ci, c1 = (__ldg(P.w_start + oxb) + __ldg(P.w_size + oxb)) * Ci;
   const int nr = r1 - r0, nc = c1 - c0;
   const int pct = nc + (KW - 1) * Ci;      // patch columns touched
-  const int lead = (sizeof(in_t) == 4 && P.vec_load) ? (c0 & 3) : 0;  // aligned patches start `lead` columns early
+  const int lead = P.vec_load ? (c0 & 3) : 0;  // aligned patches start `lead` columns early
 
   // ---- per-row (VR = 1) / per-group (VR = 4) records for stage 2
   if (tid < TY) {
@@ -182,6 +182,40 @@ __global__ void __launch_bounds__(NT, GEN ? 2 : (KH <= 3 && VR == 1 ? 8 : 5)) aa
       }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
+    } else if (P.vec_load) {
+      // uint8, rows 4-byte aligned: one 32-bit load = 4 pixels -> PRMT/FADD conversion -> one 128-bit shared store
+      // (byte loads made the uint8 upsampling shapes patch-load-bound: 0.34-0.42 of peak where fp32 reaches 0.8).
+      // Groups that would cross the end of the row (the tensor may end there) are read byte by byte.
+      const in_t* srca = src - lead;
+      const int nq = P.pcp >> 2;                       // 4-pixel groups per patch row
+      const int nca = lead + nc;                       // valid elements per patch row
+      const int row_left = P.in_wf - (c0 - lead);      // elements from the patch's first column to the end of the row
+      const int total = nr * nq;
+      constexpr int B = 4;
+      for (int i0 = tid; i0 < total; i0 += NT * B) {
+        uint32_t wv[B];
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+          const int i = i0 + j * NT;
+          const int r = i / nq, q = i - r * nq;
+          wv[j] = 0u;
+          if (i < total && 4 * q < nca) {
+            const in_t* g = srca + (int64_t)r * P.lin.stride_h + 4 * q;
+            if (4 * q + 4 <= row_left) wv[j] = __ldg(reinterpret_cast<const uint32_t*>(g));
+            else
+              for (int e = 0; 4 * q + e < row_left; e++) wv[j] |= (uint32_t)__ldg(g + e) << (8 * e);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+          const int i = i0 + j * NT;
+          if (i < total) {
+            float f[4];
+            aa_unpack4(wv[j], f);
+            *reinterpret_cast<float4*>(patch + 4 * i) = make_float4(f[0], f[1], f[2], f[3]);
+          }
+        }
+      }
     } else {
       constexpr int B = 8;
       const int ncol_it = (pct + TXV - 1) / TXV;       // column iterations per row
@@ -461,7 +495,7 @@ int launch_tile(const void* in, int in_dtype, const Layout& lin, void* out, cons
       return fail(AA_ERR_UNSUPPORTED, "tile: input patch too large; use the streaming/general path");
     }
   }
-  P.vec_load = in_dtype == AA_F32 && ((uintptr_t)in) % 16 == 0 && lin.stride_h % 4 == 0 && lin.stride_n % 4 == 0 &&
+  P.vec_load = ((uintptr_t)in) % (in_dtype == AA_F32 ? 16 : 4) == 0 && lin.stride_h % 4 == 0 && lin.stride_n % 4 == 0 &&
                (lin.Cp == 1 || lin.stride_p % 4 == 0);
   P.dci = FastDiv::make((uint32_t)Ci);
   P.dcp = FastDiv::make((uint32_t)(lin.Cp > 0 ? lin.Cp : 1));

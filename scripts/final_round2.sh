@@ -8,6 +8,7 @@ timeout 300 python bench.py --config cfg3 > gpurun_out/bench_r02_final_cfg3.json
 timeout 300 python bench.py --config cfg4 > gpurun_out/bench_r02_final_cfg4.json 2>> gpurun_out/bench_r02_final.err
 timeout 600 python scripts/bench_sweep.py > gpurun_out/r02_sweep_1gpu.txt 2>&1
 timeout 300 python scripts/strong_probe.py > gpurun_out/r02_strong_probe.txt 2>&1
+timeout 300 python scripts/redo_cost_probe.py > gpurun_out/r02_drain_cost.txt 2>&1
 B="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-sub"
 timeout 300 $B --config cfg3 > gpurun_out/r02_plain_cfg3.log 2>&1 &&
 timeout 400 ncu --set full --clock-control none --import-source on -f -k regex:aa_vmma -s 3 -c 1 -o gpurun_out/prof_r02_cfg3_vmma_full $B --config cfg3 > gpurun_out/r02_ncu_f3.log 2>&1
