@@ -94,7 +94,7 @@ bool vmma_auto(const AxisTables* th, const AxisTables* tw) {
   if (mode == 0) return false;
   if (mode == 1) return true;
   (void)tw;
-  // measured on the uint8 sweep (profiles/r02_u8_probe.txt -> DESIGN.md section 6): the tensor-core kernel beats the
+  // measured on the uint8 sweep (profiles/r02_u8_paths.txt -> DESIGN.md section 6): the tensor-core kernel beats the
   // streaming, band and tile kernels at every vertical scale from 1x down to the 7x its K span allows -- except bilinear at
   // exactly 1x, where the band kernel with 32-bit pixel loads is 13 % faster (3-tap windows: nothing to amortise)
   if (th->scale_f <= 1.0f && th->xsize_max <= 3) return false;
