@@ -31,6 +31,17 @@ def test_header_symbols_exported():
     assert L.aa_abi_version() == 2
 
 
+def test_flag_constants_match_header():
+    """The ctypes binding's flag values are the header's #defines (a drifted constant would silently select another path)."""
+    from interpolate_antialiasing_b200 import capi
+    src = open(os.path.join(ROOT, "include", "aa_resize.h")).read()
+    flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+AA_FLAG_(\w+)\s+(\d+)u", src)}
+    assert len(flags) >= 9
+    for name, val in flags.items():
+        assert getattr(capi, "FLAG_" + name) == val, name
+    assert len(set(v for v in flags.values() if v)) == len([v for v in flags.values() if v])  # distinct bits
+
+
 def test_no_oracle_in_product_path():
     """The product must not route through the oracle or any CPU fallback."""
     pkg = os.path.join(ROOT, "interpolate_antialiasing_b200")
