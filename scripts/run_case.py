@@ -1,5 +1,5 @@
 """Runs one forward/backward case a few times (for `ncu -k regex:...`).
-usage: python scripts/run_case.py fwd|bwd mode C cl H W oH oW [N]"""
+usage: python scripts/run_case.py fwd|bwd|fwd8 mode C cl H W oH oW [N]      (fwd8 = uint8 input)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,8 +8,9 @@ kind, mode, C, cl, H, W, oH, oW = sys.argv[1], sys.argv[2], int(sys.argv[3]), in
 N = int(sys.argv[9]) if len(sys.argv) > 9 else max(1, int(2.5e8 // (C * (H * W + oH * oW) * 4)))
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev).manual_seed(0)
-if kind == "fwd":
+if kind in ("fwd", "fwd8"):
     x = torch.rand((N, C, H, W), generator=g, device=dev) * 255
+    if kind == "fwd8": x = x.byte()
     if cl: x = x.contiguous(memory_format=torch.channels_last)
     out = capi.resize_forward(x, (oH, oW), mode)
     for _ in range(4): capi.resize_forward(x, (oH, oW), mode, out=out)
