@@ -135,9 +135,14 @@ int two_pass(const aa_tensor_desc* in, const aa_tensor_desc* out, const Layout& 
              int filter, int align, uint32_t flags, const OutEpi& epi, cudaStream_t stream) {
   if (epi.planar) return fail(AA_ERR_UNSUPPORTED, "two-pass: planar epilogue not supported");
   int rc;
-  std::shared_ptr<AxisTables> ih, iw;  // identities: H -> H and oW -> oW
-  if ((rc = get_axis_tables(in->device, in->h, in->h, filter, align, AA_F32, 0.0, stream, &ih)) != AA_OK) return rc;
-  if ((rc = get_axis_tables(in->device, out->w, out->w, filter, align, AA_F32, 0.0, stream, &iw)) != AA_OK) return rc;
+  // identities H -> H and oW -> oW: the box filter at scale 1 (window = the pixel itself, weight exactly 1).  The
+  // triangle / cubic tables at scale 1 would also be exact copies for finite data, but their windows hold zero-weight
+  // neighbours, and 0 * NaN there spreads a non-finite pixel along the axis the pass is not supposed to touch (found by
+  // scripts/fuzz_parity.py; the reference's two passes each work on one axis only, aa_interpolation_impl.h:655-679)
+  (void)filter; (void)align;
+  std::shared_ptr<AxisTables> ih, iw;
+  if ((rc = get_axis_tables(in->device, in->h, in->h, AA_FILTER_BOX, 0, AA_F32, 0.0, stream, &ih)) != AA_OK) return rc;
+  if ((rc = get_axis_tables(in->device, out->w, out->w, AA_FILTER_BOX, 0, AA_F32, 0.0, stream, &iw)) != AA_OK) return rc;
   // intermediate [n, c, H, oW] float32 in the input's memory format, dense
   Layout lt = lin;
   const int64_t row = out->w * lin.Ci;
@@ -213,7 +218,7 @@ int forward_impl(const aa_tensor_desc* in, const aa_tensor_desc* out, int filter
     if (rc != AA_ERR_UNSUPPORTED || (flags & (AA_FLAG_FORCE_STREAM | AA_FLAG_VMMA))) return rc;
     // No fused kernel takes this shape (typically: upsampling in H, many-tap downsampling in W).  Two launches with
     // an intermediate, the reference's own structure (W pass into a temp, then H pass: aa_interpolation_impl.h:655-679),
-    // each through a fused kernel with the identity on the other axis (weights {1, 0}: exact).
+    // each through a fused kernel with the identity on the other axis (one tap of weight 1: exact).
     rc = two_pass(in, out, lin, lout, th.get(), tw.get(), filter, align, flags, epi, stream);
     if (rc != AA_ERR_UNSUPPORTED) return rc;
   } else if (flags & AA_FLAG_FORCE_STREAM) {

@@ -43,6 +43,10 @@ while time.time() - t0 < budget:
     cl = rnd.random() < 0.5
     dt = rnd.choice([torch.float32, torch.float32, torch.uint8, torch.float64])
     x = (torch.rand((N, C, H, W), generator=g, dtype=torch.float64) * 255).to(dt)
+    nonfinite = dt == torch.float32 and rnd.random() < 0.3  # a few NaN/Inf pixels: their placement must be the oracle's
+    if nonfinite:
+        for _ in range(rnd.randint(1, 4)):
+            x[rnd.randrange(N), rnd.randrange(C), rnd.randrange(H), rnd.randrange(W)] = rnd.choice([float("nan"), float("inf"), float("-inf")])
     ref_in = x.double().numpy() if dt == torch.float64 else x.float().numpy()
     want = O.forward(ref_in, (oH, oW), mode, align)
     xc = x.to(dev)
@@ -62,6 +66,17 @@ while time.time() - t0 < budget:
             print("ERROR", pname, (N, C, H, W), (oH, oW), mode, align, cl, dt, e); fails += 1; continue
         got = y.cpu().numpy()
         n += 1; stats[pname] += 1
+        if nonfinite:
+            wbad = ~np.isfinite(want)
+            ok = np.array_equal(~np.isfinite(got), wbad)
+            if ok and pname == "general":
+                ok = np.array_equal(got[~wbad], want[~wbad])
+            elif ok:
+                ok = bool(np.all(np.abs(got[~wbad].astype(np.float64) - want[~wbad]) <= 1e-3 + 1e-5 * np.abs(want[~wbad])))
+            if not ok:
+                fails += 1
+                print("NONFINITE MISMATCH", pname, (N, C, H, W), (oH, oW), mode, align, cl, int((~np.isfinite(got)).sum()), int(wbad.sum()))
+            continue
         if pname == "general":
             ok = np.array_equal(got, want)
         else:
@@ -71,7 +86,7 @@ while time.time() - t0 < budget:
             fails += 1
             print("MISMATCH", pname, (N, C, H, W), (oH, oW), mode, align, cl, dt, float(np.abs(got.astype(np.float64) - want).max()))
     # backward (true adjoint) on a fraction of cases
-    if dt != torch.uint8 and rnd.random() < 0.4:
+    if dt != torch.uint8 and not nonfinite and rnd.random() < 0.4:
         go = torch.rand((N, C, oH, oW), generator=g, dtype=torch.float64).to(dt)
         wantg = O.backward_adjoint(go.numpy(), (N, C, H, W), mode, align)
         gc = go.to(dev)

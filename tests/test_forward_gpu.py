@@ -163,7 +163,8 @@ def test_nonfinite_placement_tile_band_stream(cuda):
     g = torch.Generator().manual_seed(17)
     for (H, W), osize, mode in [((40, 60), (80, 120), "cubic"), ((64, 96), (48, 72), "cubic"), ((64, 96), (48, 72), "linear"),
                                 ((120, 160), (30, 40), "linear"), ((120, 160), (24, 50), "cubic"), ((50, 70), (50, 70), "linear"),
-                                ((96, 64), (40, 150), "cubic"), ((64, 96), (100, 30), "linear"), ((300, 420), (37, 53), "cubic")]:
+                                ((96, 64), (40, 150), "cubic"), ((64, 96), (100, 30), "linear"), ((300, 420), (37, 53), "cubic"),
+                                ((24, 160), (72, 80), "cubic"), ((48, 200), (120, 60), "cubic")]:  # the last two: two launches
         x = torch.rand((2, 3, H, W), generator=g) * 255
         for (n, c, y, xx), val in [((0, 0, 5, 7), float("nan")), ((0, 2, H - 1, W - 1), float("inf")), ((1, 1, H // 2, W // 3), float("-inf")),
                                    ((1, 0, 0, 0), float("nan"))]:
