@@ -88,6 +88,10 @@ while time.time() - t0 < budget:
     # backward (true adjoint) on a fraction of cases
     if dt != torch.uint8 and not nonfinite and rnd.random() < 0.4:
         go = torch.rand((N, C, oH, oW), generator=g, dtype=torch.float64).to(dt)
+        gnf = dt == torch.float32 and rnd.random() < 0.3  # non-finite gradients: placement must be the oracle's
+        if gnf:
+            for _ in range(rnd.randint(1, 3)):
+                go[rnd.randrange(N), rnd.randrange(C), rnd.randrange(oH), rnd.randrange(oW)] = rnd.choice([float("nan"), float("inf"), float("-inf")])
         wantg = O.backward_adjoint(go.numpy(), (N, C, H, W), mode, align)
         gc = go.to(dev)
         if cl:
@@ -96,7 +100,13 @@ while time.time() - t0 < budget:
         gi = capi.resize_backward(gc, (N, C, H, W), mode, align)
         torch.cuda.synchronize()
         n += 1
-        if not np.allclose(gi.cpu().numpy(), wantg, rtol=1e-5, atol=4e-6 if dt == torch.float32 else 1e-11):
+        if gnf:
+            gbad = ~np.isfinite(wantg)
+            gnp = gi.cpu().numpy()
+            if not np.array_equal(~np.isfinite(gnp), gbad) or not np.allclose(gnp[~gbad], wantg[~gbad], rtol=1e-5, atol=4e-6):
+                fails += 1
+                print("BWD NONFINITE MISMATCH", (N, C, H, W), (oH, oW), mode, align, cl, int((~np.isfinite(gnp)).sum()), int(gbad.sum()))
+        elif not np.allclose(gi.cpu().numpy(), wantg, rtol=1e-5, atol=4e-6 if dt == torch.float32 else 1e-11):
             fails += 1
             print("BWD MISMATCH", (N, C, H, W), (oH, oW), mode, align, cl, dt, float(np.abs(gi.cpu().numpy() - wantg).max()))
 print(f"fuzz: {n} checks in {time.time() - t0:.0f}s, {fails} failures, per path {stats}")
