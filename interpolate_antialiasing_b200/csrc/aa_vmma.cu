@@ -84,6 +84,7 @@ struct VParams {
   int prof;
   int hr;  // rows per thread in the horizontal pass (2, 4 or 8)
   int vt;  // V chunk rotation shift (31 = none), see vchunk()
+  int stagger;  // cycles the odd epilogue groups wait after every strip change (de-phases the groups), 0 = none
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -409,6 +410,13 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
         strip_setup(P.S, tc, NTC, it.ox0, it.ox1, Wp, pinfo, &strip_fl0, &strip_npc);
         cur_strip = it.strip;
         consumer_sync();
+        // The groups leave this barrier in lock-step: all four would read TMEM together and then gather from shared
+        // memory together.  Holding the odd groups back puts their gather next to the even groups' epilogue for the 16
+        // items until the next strip change (cfg3: 1.041 -> 1.022 ms at 1000 cycles; 2000: 1.025, 3000: 1.032, 4500: 1.051).
+        if (P.stagger > 0 && (half & 1)) {
+          const long long t0 = clock64();
+          while (clock64() - t0 < (long long)P.stagger) {}
+        }
       }
       for (int s = 0; s < it.ntiles; s++) {
         if (ok) ok = mbar_wait(W, tfull0 + 8 * acc, aphase, 6);
@@ -716,6 +724,8 @@ int launch_vmma(const void* in, const Layout& lin, void* out, const Layout& lout
   // group: latency-bound); narrow strips take 2 rows so that all four warps of a group have work
   debug_env("AA_VMMA_R", ((pl.strip_ox + 1) / 2) * Ci > 16 ? 4 : 2, &v);
   P.hr = (int)v;
+  debug_env("AA_VMMA_STAGGER", 1000, &v);
+  P.stagger = (int)v;
   debug_env("AA_VMMA_PROF", 0, &v);
   P.prof = (int)v;
   debug_env("AA_VMMA_TIMEOUT_MS", 2000, &v);
