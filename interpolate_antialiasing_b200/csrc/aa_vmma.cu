@@ -56,7 +56,8 @@ constexpr int VCOLS = MAX_TILES * TILE_M;    // 512 flat columns of vertically f
 constexpr int VPITCH = OYB + 4;              // floats per column of V (pad: conflict-free 128-bit stores)
 constexpr int VPADC = 32;                    // extra V columns a lane may read past its own window (zero weights, finite data)
 constexpr int VALLOC = VCOLS + VPADC;
-constexpr int NACC = 4;                      // accumulator buffers in TMEM (128 columns each)
+constexpr int NACC = 5;                      // accumulator buffers in TMEM
+constexpr int ACC_COLS = 96;                 // columns per buffer (= UMMA_N); 5 x 96 = 480 of the 512 allocated
 constexpr int MAX_KSTEPS = 8;
 constexpr int NWC = 16, NTC = NWC * 32, NT = NTC + 64;  // 16 epilogue warps + producer + MMA issuer
 constexpr int NGRP = 4, GROWS = OYB / NGRP;             // 4 independent epilogue groups of 4 warps, 8 output rows each
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
           ok = mbar_wait(W, tempty0 + 8 * acc, aphase ^ 1, 4);
           if (!ok) break;
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * (uint32_t)ACC_COLS;
           ok = mbar_wait(W, full0 + 8 * stage, phase, 5);
           if (!ok) break;
           tc_fence_after();
@@ -412,7 +413,9 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
         consumer_sync();
         // The groups leave this barrier in lock-step: all four would read TMEM together and then gather from shared
         // memory together.  Holding the odd groups back puts their gather next to the even groups' epilogue for the 16
-        // items until the next strip change (cfg3: 1.041 -> 1.022 ms at 1000 cycles; 2000: 1.025, 3000: 1.032, 4500: 1.051).
+        // items until the next strip change.  cfg3, four accumulator buffers: 1.041 -> 1.022 ms at 1000 cycles (2000: 1.025,
+        // 3000: 1.032, 4500: 1.051 -- a group further behind than the ring allows stalls the MMA warp); five buffers:
+        // 1.046 -> 1.012 ms at 2000-2500 cycles (1000: 1.025, 3000: 1.018).
         if (P.stagger > 0 && (half & 1)) {
           const long long t0 = clock64();
           while (clock64() - t0 < (long long)P.stagger) {}
@@ -427,7 +430,7 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
         } else if (ok) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + half * GROWS);
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + half * GROWS);
           int l0[GROWS], l1[GROWS], l2[GROWS];
           const long long t_e0 = kProf && P.prof ? clock64() : 0;
           tmem_ld8(taddr, l0);
@@ -724,7 +727,7 @@ int launch_vmma(const void* in, const Layout& lin, void* out, const Layout& lout
   // group: latency-bound); narrow strips take 2 rows so that all four warps of a group have work
   debug_env("AA_VMMA_R", ((pl.strip_ox + 1) / 2) * Ci > 16 ? 4 : 2, &v);
   P.hr = (int)v;
-  debug_env("AA_VMMA_STAGGER", 1000, &v);
+  debug_env("AA_VMMA_STAGGER", 2200, &v);
   P.stagger = (int)v;
   debug_env("AA_VMMA_PROF", 0, &v);
   P.prof = (int)v;
