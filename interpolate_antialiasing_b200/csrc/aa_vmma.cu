@@ -30,9 +30,10 @@
 //   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=96, K=32) per stage and
 //              tcgen05.commit to release stages / publish accumulators
 //   warps 2-17 epilogue + horizontal pass: 4 independent groups of 4 warps (one per TMEM lane quarter), 8 rows each
-// Work item = (plane, column strip of <= 512 flat input columns, block of 32 output rows), ordered so that
-// consecutive items of a CTA share the strip and walk DOWN the image: the 2*support halo rows an item
-// shares with its predecessor were fetched by the same SM a few microseconds earlier and hit in L2.
+// Work item = (column strip of <= 512 flat input columns, plane, block of 32 output rows), numbered in that order with
+// the row block fastest: consecutive items of a CTA walk DOWN one strip of one plane (part of the 2*support halo rows an
+// item shares with its predecessor are L2 hits), then take the same strip of the next plane, so a CTA's whole range
+// lies in one or two strips and the strip's horizontal tables are set up once or twice per CTA.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -191,21 +192,27 @@ __device__ __forceinline__ void item_strip(const VParams& P, Item& it) {  // geo
   const int fl_end = (__ldg(P.S.xmin_w + it.ox1 - 1) + __ldg(P.S.xsize_w + it.ox1 - 1)) * P.S.Ci;
   it.ntiles = (fl_end - it.fl0 + TILE_M - 1) / TILE_M;
 }
-// items are numbered (plane, strip, oyb) with oyb fastest
+// items are numbered (strip, plane, oyb) with oyb fastest: a CTA walks down one strip of one plane (part of the halo rows
+// of consecutive items are L2 hits), then takes the same strip of the next plane -- its range of items touches one or two
+// strips, so the strip tables (Wp, pinfo) and the all-warps barrier that guards them are set up once or twice per CTA
+// instead of once per 16 items (cfg3 1.012 -> 0.96-0.97 ms, the uint8 sweep 0.415 -> 0.435 of peak).  With the plane
+// fastest instead ((strip, oyb, plane): the weight matrix B would change once per CTA, not per item) the halo reuse is
+// lost: 0.7 % slower on cfg3, 1.2 % on the sweep, same-box A/B.
 __device__ __forceinline__ Item item_first(const VParams& P, int64_t i) {
   Item it;
   const int64_t t = i / P.n_oyb;
   it.oyb = (int)(i - t * P.n_oyb);
-  it.plane = t / P.S.n_strips;
-  it.strip = (int)(t - it.plane * P.S.n_strips);
+  it.strip = (int)(t / P.S.lin.planes);
+  it.plane = t - (int64_t)it.strip * P.S.lin.planes;
   item_strip(P, it);
   return it;
 }
 __device__ __forceinline__ void item_next(const VParams& P, Item& it) {
   if (++it.oyb < P.n_oyb) return;
   it.oyb = 0;
-  if (++it.strip == P.S.n_strips) { it.strip = 0; it.plane++; }
-  item_strip(P, it);
+  if (++it.plane < P.S.lin.planes) return;
+  it.plane = 0;
+  if (++it.strip < P.S.n_strips) item_strip(P, it);  // (past the last item: nothing to look up)
 }
 
 // Horizontal pass of one epilogue group over its 16 rows of the transposed buffer V[flat column][VPITCH]: one work
@@ -346,12 +353,16 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
       uint32_t phase = 0, bphase = 0;
       bool ok = true;
       Item it = item_first(P, i_begin);
+      int b_oyb = -1;  // row block whose weight matrix was copied last
       for (int64_t i = i_begin; i < i_end && ok; i++, item_next(P, it)) {
-        ok = mbar_wait(W, bempty0 + 8 * bslot, bphase ^ 1, 1);
-        if (!ok) break;
-        mbar_expect_tx(bfull0 + 8 * bslot, (uint32_t)P.b_bytes);
-        bulk_g2s(sB + (uint32_t)bslot * P.b_bytes, P.bq + (size_t)it.oyb * P.b_bytes, (uint32_t)P.b_bytes, bfull0 + 8 * bslot);
-        if (++bslot == 2) { bslot = 0; bphase ^= 1; }
+        if (it.oyb != b_oyb) {
+          ok = mbar_wait(W, bempty0 + 8 * bslot, bphase ^ 1, 1);
+          if (!ok) break;
+          mbar_expect_tx(bfull0 + 8 * bslot, (uint32_t)P.b_bytes);
+          bulk_g2s(sB + (uint32_t)bslot * P.b_bytes, P.bq + (size_t)it.oyb * P.b_bytes, (uint32_t)P.b_bytes, bfull0 + 8 * bslot);
+          if (++bslot == 2) { bslot = 0; bphase ^= 1; }
+          b_oyb = it.oyb;
+        }
         const int y0 = __ldg(P.S.xmin_h + it.oyb * OYBR);
         const int pc = (int)(it.plane % P.Cp_in), pn = (int)(it.plane / P.Cp_in);
         for (int s = 0; s < it.ntiles; s++) {  // one TMA box per tile: 128 flat columns x ksteps*32 rows
@@ -370,10 +381,18 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
       uint32_t phase = 0, bphase = 0, aphase = 0;
       bool ok = true;
       Item it = item_first(P, i_begin);
+      int b_oyb = -1, b_cur = -1;  // row block / slot of the weight matrix in use
+      uint64_t bdesc0 = 0;
       for (int64_t i = i_begin; i < i_end && ok; i++, item_next(P, it)) {
-        ok = mbar_wait(W, bfull0 + 8 * bslot, bphase, 3);
-        if (!ok) break;
-        const uint64_t bdesc0 = P.desc_tmpl | (uint64_t)(((sB + (uint32_t)bslot * P.b_bytes) >> 4) & 0x3FFFu);
+        if (it.oyb != b_oyb) {
+          if (b_cur >= 0) umma_commit(bempty0 + 8 * b_cur);  // the previous matrix is free once the MMAs issued so far are done
+          ok = mbar_wait(W, bfull0 + 8 * bslot, bphase, 3);
+          if (!ok) break;
+          bdesc0 = P.desc_tmpl | (uint64_t)(((sB + (uint32_t)bslot * P.b_bytes) >> 4) & 0x3FFFu);
+          b_cur = bslot;
+          b_oyb = it.oyb;
+          if (++bslot == 2) { bslot = 0; bphase ^= 1; }
+        }
         for (int s = 0; s < it.ntiles && ok; s++) {
           ok = mbar_wait(W, tempty0 + 8 * acc, aphase ^ 1, 4);
           if (!ok) break;
@@ -390,8 +409,6 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
           umma_commit(tfull0 + 8 * acc);
           if (++acc == NACC) { acc = 0; aphase ^= 1; }
         }
-        umma_commit(bempty0 + 8 * bslot);
-        if (++bslot == 2) { bslot = 0; bphase ^= 1; }
       }
     }
   } else {
