@@ -354,6 +354,8 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
       bool ok = true;
       Item it = item_first(P, i_begin);
       int b_oyb = -1;  // row block whose weight matrix was copied last
+      int pc = 0, pn = 0;  // tensor-map coordinates of the item's plane
+      int64_t tm_plane = -1;
       for (int64_t i = i_begin; i < i_end && ok; i++, item_next(P, it)) {
         if (it.oyb != b_oyb) {
           ok = mbar_wait(W, bempty0 + 8 * bslot, bphase ^ 1, 1);
@@ -364,7 +366,11 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
           b_oyb = it.oyb;
         }
         const int y0 = __ldg(P.S.xmin_h + it.oyb * OYBR);
-        const int pc = (int)(it.plane % P.Cp_in), pn = (int)(it.plane / P.Cp_in);
+        if (it.plane != tm_plane) {  // (the 64-bit divisions once per plane, not per item)
+          pc = (int)(it.plane % P.Cp_in);
+          pn = (int)(it.plane / P.Cp_in);
+          tm_plane = it.plane;
+        }
         for (int s = 0; s < it.ntiles; s++) {  // one TMA box per tile: 128 flat columns x ksteps*32 rows
           ok = mbar_wait(W, empty0 + 8 * stage, phase ^ 1, 2);
           if (!ok) break;
@@ -421,6 +427,7 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
     uint32_t aphase = 0;
     int cur_strip = -1, strip_fl0 = 0, strip_npc = 0;
     bool ok = true;
+    int64_t op = 0, op_plane = -1;  // element offset of the item's output plane
     Item it = item_first(P, i_begin);
     for (int64_t i = i_begin; i < i_end; i++, item_next(P, it)) {
       if (it.strip != cur_strip) {
@@ -488,7 +495,10 @@ __global__ void __launch_bounds__(NT, 1) aa_vmma_kernel(const __grid_constant__ 
       const long long t_h0 = kProf ? clock64() : 0;
       group_sync(half);  // this group's 16 rows of all tiles are in V
       const long long t_h1 = kProf ? clock64() : 0;
-      const int64_t op = (it.plane / P.S.lout.Cp) * P.S.lout.stride_n + (it.plane % P.S.lout.Cp) * P.S.lout.stride_p;
+      if (it.plane != op_plane) {  // 16 consecutive items share the plane: the 64-bit divisions once per plane, not per item
+        op = (it.plane / P.S.lout.Cp) * P.S.lout.stride_n + (it.plane % P.S.lout.Cp) * P.S.lout.stride_p;
+        op_plane = it.plane;
+      }
       const int nrows = min(OYBR, (int)P.S.oH - it.oyb * OYBR);
       // rows per thread: the pass is bound by shared-memory bandwidth (2 B of V per FMA for a column pair + 4/R B of
       // weights), so more rows per thread is less traffic; fewer rows only when the strip is too narrow to occupy the warps
