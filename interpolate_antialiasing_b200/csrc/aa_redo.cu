@@ -109,18 +109,10 @@ int redo_list(int device, cudaStream_t stream, RedoList** out) {
   return AA_OK;
 }
 
-void redo_clear() {
-  std::lock_guard<std::mutex> lock(g_mu);
-  for (auto& ch : g_chunks) {
-    int cur = 0;
-    cudaGetDevice(&cur);
-    cudaSetDevice(ch.device);
-    cudaFree(ch.base);  // synchronises: nothing queued can still use a list
-    cudaSetDevice(cur);
-  }
-  g_chunks.clear();
-  g_lists.clear();
-}
+// aa_clear_table_cache: the lists are NOT freed.  A call on another thread may hold a list pointer it has not launched with
+// yet (tables are reference-counted for exactly that case; lists are plain device memory), and there is nothing to gain:
+// a list is 64 KB and their number is bounded by the number of distinct (device, stream) pairs the process ever used.
+void redo_clear() {}
 
 bool redo_set_enabled(bool on) {  // per calling thread: AA_FLAG_ASSUME_FINITE switches the drain launch off for one call
   const bool was = t_redo_enabled;
