@@ -86,6 +86,7 @@ struct VParams {
   int prof;
   int hr;  // rows per thread in the horizontal pass (2, 4 or 8)
   int vt;  // V chunk rotation shift (31 = none), see vchunk()
+  int st2;  // fp32 planar output whose base pointer and strides are all even: column pairs go out as 64-bit stores
   int stagger;  // cycles the odd epilogue groups wait after every strip change (de-phases the groups), 0 = none
 };
 
@@ -281,11 +282,19 @@ __device__ __forceinline__ void hphase_T(const VParams& P, const float* __restri
       const int64_t dst = op_off + (int64_t)(oy0 + r0) * osh + pi.w;
       const bool hasb = ((pi.z >> 16) & 1) != 0;
       const int c = pi.z >> 20, cstep = P.S.epi.colstep(Ci);
+      // planar fp32 output, both columns of the pair present, 8-byte aligned: one 64-bit store per row instead of two 32-bit
+      // ones (P.st2: base pointer and all strides are even, checked on the host; the pair's own column offset here)
+      if (!GEN && P.st2 && hasb && Ci == 1 && ((dst & 1) == 0) && r0 + R <= nrows) {
+        float* o = reinterpret_cast<float*>(P.S.out) + dst;
 #pragma unroll
-      for (int r = 0; r < R; r++) {
-        if (r0 + r < nrows) {
-          aa_store<GEN>(P.S.out, dst + (int64_t)r * osh, h[r].x, c, P.S.epi);
-          if (hasb) aa_store<GEN>(P.S.out, dst + (int64_t)r * osh + cstep, h[r].y, c, P.S.epi);
+        for (int r = 0; r < R; r++) *reinterpret_cast<float2*>(o + (int64_t)r * osh) = h[r];
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          if (r0 + r < nrows) {
+            aa_store<GEN>(P.S.out, dst + (int64_t)r * osh, h[r].x, c, P.S.epi);
+            if (hasb) aa_store<GEN>(P.S.out, dst + (int64_t)r * osh + cstep, h[r].y, c, P.S.epi);
+          }
         }
       }
     }
@@ -736,6 +745,8 @@ int launch_vmma(const void* in, const Layout& lin, void* out, const Layout& lout
   P.S.n_strips = pl.n_strips; P.S.strip_ox = pl.strip_ox; P.S.kp = pl.kp; P.S.wtab_bytes = pl.wtab_bytes;
   P.nstage = pl.nstage;
   P.vt = pl.vt;
+  P.st2 = (!gen && epi.kind == 0 && !epi.planar && Ci == 1 && ((uintptr_t)out) % 8 == 0 && lout.stride_h % 2 == 0 && lout.stride_n % 2 == 0 &&
+           (lout.Cp == 1 || lout.stride_p % 2 == 0)) ? 1 : 0;
   P.total_items = lin.planes * pl.n_strips * P.n_oyb;
   P.dbg = g_dbg[th->device];
 
