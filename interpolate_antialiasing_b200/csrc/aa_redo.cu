@@ -5,6 +5,7 @@
 // zero-weight neighbours (see aa_common.cuh, "non-finite inputs").  A CTA of a fast kernel that stored a
 // non-finite value appends its region to the stream's RedoList; this kernel re-evaluates the listed regions with
 // in-window taps only.  With an empty list -- every finite image -- each CTA reads one counter and exits.
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -89,9 +90,18 @@ constexpr int kChunk = 32;
 int redo_list(int device, cudaStream_t stream, RedoList** out) {
   *out = nullptr;  // AA_FLAG_ASSUME_FINITE: no list -- the kernels then report nothing, and nothing stale is left for a later drain
   if (!t_redo_enabled) return AA_OK;
+  // steady state: the calling thread asks for the same (device, stream) as last time -- no lock, no map lookup (lists are never freed)
+  thread_local int last_dev = -1;
+  thread_local cudaStream_t last_stream = nullptr;
+  thread_local RedoList* last_list = nullptr;
+  if (last_list && last_dev == device && last_stream == stream) { *out = last_list; return AA_OK; }
   std::lock_guard<std::mutex> lock(g_mu);
   auto it = g_lists.find({device, stream});
-  if (it != g_lists.end()) { *out = it->second; return AA_OK; }
+  if (it != g_lists.end()) {
+    *out = it->second;
+    last_dev = device; last_stream = stream; last_list = it->second;
+    return AA_OK;
+  }
   Chunk* c = nullptr;
   for (auto& ch : g_chunks)
     if (ch.device == device && ch.used < kChunk) { c = &ch; break; }
@@ -106,6 +116,7 @@ int redo_list(int device, cudaStream_t stream, RedoList** out) {
   RedoList* L = c->base + c->used++;
   g_lists[{device, stream}] = L;
   *out = L;
+  last_dev = device; last_stream = stream; last_list = L;
   return AA_OK;
 }
 
@@ -122,16 +133,11 @@ bool redo_set_enabled(bool on) {  // per calling thread: AA_FLAG_ASSUME_FINITE s
 
 int launch_redo(const RedoParams& R, int device, cudaStream_t stream) {
   if (!R.list) return AA_OK;
-  static std::mutex mu;
-  static int sms[64] = {0};
-  int n = 0;
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    if (device >= 0 && device < 64) n = sms[device];
-    if (!n) {
-      AA_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
-      if (device >= 0 && device < 64) sms[device] = n;
-    }
+  static std::atomic<int> sms[64];  // SM count per device (0 = not asked yet; racing first calls ask twice, harmlessly)
+  int n = (device >= 0 && device < 64) ? sms[device].load(std::memory_order_relaxed) : 0;
+  if (!n) {
+    AA_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+    if (device >= 0 && device < 64) sms[device].store(n, std::memory_order_relaxed);
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)n);
