@@ -18,17 +18,18 @@
 //     accumulate exactly in int32 in TMEM, so the vertical pass is exact up to the 2^-s weight
 //     quantisation (s = 22..30: <= 7e-5 on a 0..255 scale in the worst case, far inside the
 //     1e-3 + 1e-5*|x| contract and below the fp32 rounding of the reference's own pass);
-//   * four epilogue warp pairs read the accumulators (tcgen05.ld), rebuild fp32 from the three limbs with
+//   * four epilogue groups of four warps read the accumulators (tcgen05.ld), rebuild fp32 from the three limbs with
 //     three integer adds + three FFMA2 per two values (magic-number int->float, no I2F), and store the
 //     vertically filtered rows TRANSPOSED ([flat column][32 output rows]) in shared memory;
 //   * the HORIZONTAL pass is the same pair-of-columns gather as aa_stream_common.cuh, but one 128-bit
 //     LDS now feeds four output rows (4x fewer shared-memory loads than the row-major buffer).
 //
 // Roles (576 threads, one CTA per SM, persistent over a contiguous range of work items):
-//   warp 0     TMA producer: cp.async.bulk.tensor (4-D map: flat x, y, channel plane, image) into a ring
-//              of 4 KB stages + one bulk copy of the item's weight limbs; mbarrier complete_tx
-//   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=96, K=32) per stage and
-//              tcgen05.commit to release stages / publish accumulators
+//   warp 0     TMA producer: cp.async.bulk.tensor (4-D map: flat x, y, channel plane, image), one box = the whole K span
+//              of a 128-column tile, into a ring of stages + one bulk copy of the weight limbs whenever the row block
+//              changes; mbarrier complete_tx
+//   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=96, K=32) per 32 rows of a stage and
+//              tcgen05.commit to release stages / publish accumulators (a ring of 5 accumulator buffers in TMEM)
 //   warps 2-17 epilogue + horizontal pass: 4 independent groups of 4 warps (one per TMEM lane quarter), 8 rows each
 // Work item = (column strip of <= 512 flat input columns, plane, block of 32 output rows), numbered in that order with
 // the row block fastest: consecutive items of a CTA walk DOWN one strip of one plane (part of the 2*support halo rows an
