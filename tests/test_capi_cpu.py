@@ -135,3 +135,35 @@ def test_stream_kernels_issue_row_loads_before_first_fma():
     assert flagged and all(l.startswith("A=6 VEC=8 h") for l in flagged) or not flagged, "\n".join(flagged)
     assert any(l.startswith("A=3 VEC=4 f NT=256 U=4 GEN=0 PAD=0 PF=0: 4 data loads") for l in r.stdout.splitlines())
     assert any(l.startswith("A=3 VEC=4 f NT=256 U=4 GEN=0 PAD=0 PF=1: 4 data loads") for l in r.stdout.splitlines())
+
+
+def test_sass_of_the_built_kernels():
+    """What the built sm_100a library actually contains (cuobjdump on the .so, no GPU needed):
+    the uint8 kernel issues tcgen05 MMAs (UTCIMMA), TMA tensor copies (UTMALDG) and TMEM loads (LDTM); the drain kernel
+    that follows every fast float launch exists and waits on its programmatic dependency (ACQBULK = griddepcontrol.wait; the float
+    tile kernels trigger it with PREEXIT = griddepcontrol.launch_dependents);
+    the headline streaming instantiation keeps everything in registers (no local-memory loads or stores)."""
+    import subprocess
+    from interpolate_antialiasing_b200 import capi
+    out = subprocess.run(["cuobjdump", "-sass", capi.LIB], capture_output=True, text=True, timeout=600).stdout
+    funcs, cur = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            funcs[cur] = []
+        elif cur and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+            funcs[cur].append(line.split("*/", 1)[1].strip())
+    vmma = [f for f in funcs if "aa_vmma_kernel" in f]
+    assert vmma
+    for f in vmma:
+        text = "\n".join(funcs[f])
+        assert "UTCIMMA" in text and "UTMALDG" in text and "LDTM" in text, f
+    redo = [f for f in funcs if "aa_redo_kernel" in f]
+    assert len(redo) == 2
+    assert all(any(i.startswith("ACQBULK") for i in funcs[f]) for f in redo)                 # griddepcontrol.wait
+    tile_f32 = [f for f in funcs if "aa_tile_kernel" in f and re.search(r"ELb0EfE", f)]
+    assert tile_f32 and all(any(i.startswith("PREEXIT") for i in funcs[f]) for f in tile_f32)  # griddepcontrol.launch_dependents
+    head = [f for f in funcs if re.search(r"aa_stream_kernelILi3ELi4EfLi256ELi4ELi4ELb0ELb0ELb0E", f)]
+    assert len(head) == 1
+    assert not any(i.startswith(("LDL", "STL")) for i in funcs[head[0]]), "the cfg2 streaming kernel spills"
